@@ -1,0 +1,441 @@
+// Soft/hard correspondence map: fp32 CUDA-core candidate pass, exact finalize, and the C entry point.
+//
+// Pipeline of dvm_softmap_fwd (replaces models/loss.py:91-95, 110-114, 1339-1347, 1408-1409):
+//   1. candidate pass  (tcgen05 f16/bf16 in softmap_tc.cu, or fp32 SIMT below): one sweep over all M
+//      columns per row keeps the KC=16 smallest squared distances and the softmax mass of the rest;
+//   2. finalize        : merges the partial lists of a row, re-scores the 16 candidates EXACTLY in fp32
+//      from the fp32 inputs (direct differences, the `donot_use_mm_for_euclid_dist` form), orders them
+//      (ties -> lower index), emits arg-min, top-k (idx, w, d), row statistics and Pi.V, and certifies
+//      that no discarded column can belong to the top-k given the candidate pass' error bound;
+//   3. rows that fail the certificate are recomputed by the fp32 pass (device-side list, no host sync).
+#include "softmap.cuh"
+
+namespace dvm {
+
+// =================================================================================================
+// 1. fp32 CUDA-core candidate pass
+// =================================================================================================
+constexpr int SIMT_BM = 64;       // rows per CTA
+constexpr int SIMT_BN = 64;       // columns per tile
+constexpr int SIMT_CG = 4;        // column groups (threads per row) -> P = 4 partial lists per row
+constexpr int SIMT_CPT = SIMT_BN / SIMT_CG;   // 16 columns per thread per tile
+constexpr int SIMT_THREADS = SIMT_BM * SIMT_CG;
+
+template <bool kSoft>
+__global__ void __launch_bounds__(SIMT_THREADS)
+softmap_cand_simt_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M, int C,
+                         const int* __restrict__ row_list, const int* __restrict__ row_count,
+                         float a2, float cut_over_alpha, CandBuffers cb) {
+    extern __shared__ __align__(16) float smem[];
+    const int ld = C + 4;                        // padded row stride: conflict-free LDS.128
+    float* Xs = smem;
+    float* Ys = smem + SIMT_BM * ld;
+    __shared__ int s_rows[SIMT_BM];
+
+    const int tid = threadIdx.x;
+    const int r = tid & (SIMT_BM - 1);
+    const int cg = tid >> 6;
+    int n_rows;
+    if (row_list) {
+        n_rows = *row_count;
+        if ((int)blockIdx.x * SIMT_BM >= n_rows) return;
+        if (tid < SIMT_BM) {
+            const int e = blockIdx.x * SIMT_BM + tid;
+            s_rows[tid] = e < n_rows ? row_list[e] : -1;
+        }
+    } else {
+        if (tid < SIMT_BM) {
+            const int i = blockIdx.x * SIMT_BM + tid;
+            s_rows[tid] = i < N ? (int)blockIdx.y * N + i : -1;
+        }
+    }
+    __syncthreads();
+
+    // X tile: 64 rows x C, float4 granularity
+    const int c4 = C >> 2;
+    for (int e = tid; e < SIMT_BM * c4; e += SIMT_THREADS) {
+        const int rr = e / c4, cc = e - rr * c4;
+        const int g = s_rows[rr];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g >= 0) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)g * C) + cc);
+        *reinterpret_cast<float4*>(Xs + rr * ld + cc * 4) = v;
+    }
+    const int g_row = s_rows[r];
+    // batch of this CTA: list mode mixes batches, so Y is addressed per row
+    const int b_of_row = g_row >= 0 ? g_row / N : 0;
+    // In list mode rows of one CTA may belong to different batch elements; the Y tile is shared by the
+    // CTA, so the CTA sweeps once per distinct batch element present (usually one).
+    int b_lo = row_list ? 0x7fffffff : (int)blockIdx.y, b_hi = row_list ? -1 : (int)blockIdx.y;
+    if (row_list) {
+        for (int t = 0; t < SIMT_BM; ++t) {
+            const int g = s_rows[t];
+            if (g >= 0) { b_lo = min(b_lo, g / N); b_hi = max(b_hi, g / N); }
+        }
+    }
+
+    RowState st;
+    st.init();
+
+    for (int b = b_lo; b <= b_hi; ++b) {
+        const bool mine = (g_row >= 0) && (b_of_row == b);
+        const float* Yb = Y + (size_t)b * M * C;
+        for (int j0 = 0; j0 < M; j0 += SIMT_BN) {
+            __syncthreads();
+            for (int e = tid; e < SIMT_BN * c4; e += SIMT_THREADS) {
+                const int rr = e / c4, cc = e - rr * c4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j0 + rr < M) v = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)(j0 + rr) * C) + cc);
+                *reinterpret_cast<float4*>(Ys + rr * ld + cc * 4) = v;
+            }
+            __syncthreads();
+
+            float acc[SIMT_CPT];
+#pragma unroll
+            for (int c = 0; c < SIMT_CPT; ++c) acc[c] = 0.f;
+            const float* xr = Xs + r * ld;
+            const float* yr = Ys + (cg * SIMT_CPT) * ld;
+#pragma unroll 2
+            for (int k = 0; k < C; k += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+#pragma unroll
+                for (int c = 0; c < SIMT_CPT; ++c) {
+                    const float4 yv = *reinterpret_cast<const float4*>(yr + c * ld + k);   // warp-broadcast
+                    float d;
+                    d = xv.x - yv.x; acc[c] = fmaf(d, d, acc[c]);
+                    d = xv.y - yv.y; acc[c] = fmaf(d, d, acc[c]);
+                    d = xv.z - yv.z; acc[c] = fmaf(d, d, acc[c]);
+                    d = xv.w - yv.w; acc[c] = fmaf(d, d, acc[c]);
+                }
+            }
+            if (mine) {
+#pragma unroll
+                for (int c = 0; c < SIMT_CPT; ++c) {
+                    const int j = j0 + cg * SIMT_CPT + c;
+                    if (j < M && acc[c] < st.thr) row_state_visit<kSoft>(st, acc[c], j, a2, cut_over_alpha);
+                }
+            }
+        }
+    }
+
+    if (g_row >= 0) {
+        const size_t base = ((size_t)g_row * cb.P + cg) * KC;
+#pragma unroll
+        for (int t = 0; t < KC; ++t) { cb.key[base + t] = st.list.key[t]; cb.idx[base + t] = st.list.idx[t]; }
+        cb.l[(size_t)g_row * cb.P + cg] = st.l;
+        cb.r[(size_t)g_row * cb.P + cg] = st.r;
+    }
+}
+
+int launch_cand_simt(const float* X, const float* Y, int B, int N, int M, int C, float alpha, bool soft,
+                     const int* row_list, const int* row_count, int max_rows, CandBuffers cb, cudaStream_t st) {
+    const size_t smem = (size_t)(SIMT_BM + SIMT_BN) * (C + 4) * sizeof(float);
+    static bool attr_done[2] = {false, false};
+    auto kern = soft ? softmap_cand_simt_kernel<true> : softmap_cand_simt_kernel<false>;
+    if (!attr_done[soft]) {
+        DVM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done[soft] = true;
+    }
+    dim3 grid;
+    if (row_list) grid = dim3(ceil_div(max_rows, SIMT_BM), 1, 1);
+    else          grid = dim3(ceil_div(N, SIMT_BM), B, 1);
+    const float a2 = alpha * kLog2e;
+    const float coa = alpha > 0.f ? kExpCut / alpha : INFINITY;
+    if (!row_list) prof_begin(st);
+    kern<<<grid, SIMT_THREADS, smem, st>>>(X, Y, N, M, C, row_list, row_count, a2, coa, cb);
+    if (!row_list) prof_end(st);
+    DVM_LAUNCH_CHECK();
+    return 0;
+}
+
+// =================================================================================================
+// 2. finalize: merge partial lists, exact fp32 re-scoring, ordering, weights, certificate, Pi.V
+// =================================================================================================
+constexpr int FIN_WARPS = 8;
+
+struct FinalizeArgs {
+    const float* X; const float* Y; const float* V;
+    int B, N, M, C, Dv, topk;
+    float alpha;
+    CandBuffers cb;
+    const int* row_list; const int* row_count;     // optional subset of rows
+    const float* err_x; const float* err_ymax;     // candidate-pass distance error bounds (may be null)
+    float rel_bound;                               // + rel_bound * d16
+    int* flag_list; int* flag_count;               // rows failing the certificate (may be null)
+    int* tie_count;                                // counts uncertified rows when flag_list is null
+    int64_t* argmin; int* top_idx; float* top_w; float* top_d; float* row_min; float* row_sum; float* PiV;
+};
+
+template <bool kSoft>
+__global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(FinalizeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
+    int g;
+    if (a.row_list) {
+        if (w >= *a.row_count) return;
+        g = a.row_list[w];
+    } else {
+        if (w >= a.B * a.N) return;
+        g = w;
+    }
+    const int b = g / a.N;
+    const int P = a.cb.P;
+    const int E = P * KC;                       // <= 128
+    const float a2 = a.alpha * kLog2e;
+
+    // ---- load the partial lists: entry e = lane + 32 q
+    float ek[4]; int ei[4]; bool taken[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = lane + 32 * q;
+        ek[q] = INFINITY; ei[q] = -1; taken[q] = true;
+        if (e < E) {
+            ek[q] = a.cb.key[(size_t)g * E + e];
+            ei[q] = a.cb.idx[(size_t)g * E + e];
+            taken[q] = !(ei[q] >= 0);
+        }
+    }
+    float l_tot = 0.f, r_star = INFINITY;
+    if (kSoft) {
+        float rp = INFINITY, lp = 0.f;
+        if (lane < P) { rp = a.cb.r[(size_t)g * P + lane]; lp = a.cb.l[(size_t)g * P + lane]; }
+        r_star = rp;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r_star = fminf(r_star, __shfl_xor_sync(0xffffffffu, r_star, o));
+        float t = (lp != 0.f) ? lp * exp2f(-a2 * (rp - r_star)) : 0.f;
+        l_tot = warp_sum(t);
+    }
+
+    // ---- select the KC best of the union by (key, idx)
+    float sel_key = INFINITY; int sel_idx = -1;     // lane s (< KC) holds the s-th selected
+    for (int s = 0; s < KC; ++s) {
+        float bk = INFINITY; int bi = 0x7fffffff; int bq = -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (!taken[q] && kv_less(ek[q], ei[q], bk, bi)) { bk = ek[q]; bi = ei[q]; bq = q; }
+        float wk = bk; int wi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, wk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (kv_less(ok, oi, wk, wi)) { wk = ok; wi = oi; }
+        }
+        if (wi == 0x7fffffff) break;                                  // union exhausted (uniform)
+        if (bq >= 0 && bk == wk && bi == wi) {                        // the owner retires it (indices are unique)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q == bq) taken[q] = true;
+        }
+        if (lane == s) { sel_key = wk; sel_idx = wi; }
+    }
+    const float key16 = __shfl_sync(0xffffffffu, sel_key, KC - 1);
+    if (kSoft) {                                                      // listed but not selected: approximate terms
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (!taken[q]) t += exp2f(-a2 * (sqrtf(ek[q]) - r_star));
+        l_tot += warp_sum(t);
+    }
+
+    // ---- exact re-scoring: d2 = sum_c (x_c - y_c)^2, lane owns channels 4*lane + 128 t, butterfly sum
+    float4 xv[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int c = 4 * lane + 128 * t;
+        xv[t] = (c < a.C) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)g * a.C + c)) : make_float4(0, 0, 0, 0);
+    }
+    float my_d2 = INFINITY; int my_idx = 0x7fffffff;
+    const float* Yb = a.Y + (size_t)b * a.M * a.C;
+    for (int s = 0; s < KC; ++s) {
+        const int j = __shfl_sync(0xffffffffu, sel_idx, s);
+        if (j < 0) break;                                             // uniform
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int c = 4 * lane + 128 * t;
+            if (c < a.C) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)j * a.C + c));
+                float d;
+                d = xv[t].x - yv.x; acc = fmaf(d, d, acc);
+                d = xv[t].y - yv.y; acc = fmaf(d, d, acc);
+                d = xv[t].z - yv.z; acc = fmaf(d, d, acc);
+                d = xv[t].w - yv.w; acc = fmaf(d, d, acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == s) { my_d2 = acc; my_idx = j; }
+    }
+
+    // ---- rank the (<= 16) exact scores: (d2, idx) lexicographic
+    int rank = 0;
+#pragma unroll
+    for (int s = 0; s < KC; ++s) {
+        const float od = __shfl_sync(0xffffffffu, my_d2, s);
+        const int oi = __shfl_sync(0xffffffffu, my_idx, s);
+        rank += kv_less(od, oi, my_d2, my_idx) ? 1 : 0;
+    }
+    const bool valid = lane < KC && my_idx != 0x7fffffff;
+    if (!valid) rank = 99;
+    const float my_d = valid ? sqrtf(my_d2) : INFINITY;
+    float dmin = my_d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+
+    float my_w = 0.f, total = 1.f;
+    if (kSoft) {
+        const float e = valid ? expf(-a.alpha * (my_d - dmin)) : 0.f;
+        total = warp_sum(e);
+        if (l_tot != 0.f) total += l_tot * exp2f(-a2 * (r_star - dmin));
+        my_w = e / total;
+    }
+
+    if (valid && rank < a.topk) {
+        const size_t o = (size_t)g * a.topk + rank;
+        a.top_idx[o] = my_idx;
+        a.top_d[o] = my_d;
+        if (a.top_w) a.top_w[o] = my_w;
+        if (rank == 0) {
+            if (a.argmin) a.argmin[g] = my_idx;
+            if (a.row_min) a.row_min[g] = my_d;
+            if (a.row_sum) a.row_sum[g] = total;
+        }
+    }
+
+    // ---- certificate: every discarded column has candidate-pass distance >= sqrt(key16)
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, rank == a.topk - 1);
+        const float dk = m ? __shfl_sync(0xffffffffu, my_d, __ffs(m) - 1) : INFINITY;
+        if (lane == 0 && key16 != INFINITY) {
+            const float d16 = sqrtf(key16);
+            float bound = a.rel_bound * d16;
+            if (a.err_x) bound += a.err_x[g] + a.err_ymax[b];
+            if (!(dk < d16 - bound)) {
+                if (a.flag_list) a.flag_list[atomicAdd(a.flag_count, 1)] = g;
+                else if (a.tie_count) atomicAdd(a.tie_count, 1);
+            }
+        }
+    }
+
+    // ---- Pi . V  (10-sparse gather), lanes over the Dv output channels
+    if (kSoft && a.V && a.PiV) {
+        float wk[DVM_TOPK_MAX]; int jk[DVM_TOPK_MAX];
+#pragma unroll
+        for (int k = 0; k < DVM_TOPK_MAX; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, rank == k);
+            const int src = m ? __ffs(m) - 1 : 0;
+            wk[k] = m ? __shfl_sync(0xffffffffu, my_w, src) : 0.f;
+            jk[k] = m ? __shfl_sync(0xffffffffu, my_idx, src) : 0;
+            if (k >= a.topk) wk[k] = 0.f;
+        }
+        const float* Vb = a.V + (size_t)b * a.M * a.Dv;
+        for (int dv = lane; dv < a.Dv; dv += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < DVM_TOPK_MAX; ++k)
+                if (wk[k] != 0.f) acc = fmaf(wk[k], __ldg(Vb + (size_t)jk[k] * a.Dv + dv), acc);
+            a.PiV[(size_t)g * a.Dv + dv] = acc;
+        }
+    }
+}
+
+static int launch_finalize(const FinalizeArgs& a, bool soft, int max_rows, cudaStream_t st) {
+    const int grid = ceil_div(max_rows, FIN_WARPS);
+    if (soft) softmap_finalize_kernel<true><<<grid, FIN_WARPS * 32, 0, st>>>(a);
+    else      softmap_finalize_kernel<false><<<grid, FIN_WARPS * 32, 0, st>>>(a);
+    DVM_LAUNCH_CHECK();
+    return 0;
+}
+
+static void carve_cand(WsCarver& ws, size_t rows, int P, CandBuffers& cb) {
+    cb.P = P;
+    cb.key = ws.take<float>(rows * P * KC);
+    cb.idx = ws.take<int>(rows * P * KC);
+    cb.l = ws.take<float>(rows * P);
+    cb.r = ws.take<float>(rows * P);
+}
+
+static size_t softmap_ws_layout(void* base, size_t cap, int B, int N, int M, int C, int prec,
+                                CandBuffers* simt, CandBuffers* tc, int** flag_list, int** stats_fallback,
+                                float** err_x, float** err_ymax, void** tc_ws, size_t* tc_ws_bytes) {
+    WsCarver ws(base, cap);
+    const size_t rows = (size_t)B * N;
+    CandBuffers c1{}, c2{};
+    carve_cand(ws, rows, SIMT_CG, c1);
+    int* fl = nullptr; float* ex = nullptr; float* ey = nullptr; void* tws = nullptr; size_t tb = 0;
+    int* sf = ws.take<int>(4);
+    if (prec != DVM_PREC_FP32) {
+        carve_cand(ws, rows, tc_num_partials(B, N, M), c2);
+        fl = ws.take<int>(rows);
+        ex = ws.take<float>(rows);
+        ey = ws.take<float>(B);
+        tb = tc_workspace_bytes(B, N, M, C);
+        tws = ws.take<char>(tb);
+    }
+    if (simt) *simt = c1;
+    if (tc) *tc = c2;
+    if (flag_list) *flag_list = fl;
+    if (stats_fallback) *stats_fallback = sf;
+    if (err_x) *err_x = ex;
+    if (err_ymax) *err_ymax = ey;
+    if (tc_ws) *tc_ws = tws;
+    if (tc_ws_bytes) *tc_ws_bytes = tb;
+    return align_up(ws.off, 256);
+}
+
+}  // namespace dvm
+
+using namespace dvm;
+
+extern "C" size_t dvm_softmap_workspace_bytes(int B, int N, int M, int C, int prec) {
+    if (B <= 0 || N <= 0 || M <= 0 || C <= 0) return 0;
+    return softmap_ws_layout(nullptr, 0, B, N, M, C, prec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
+                               int B, int N, int M, int C, int Dv, float alpha, int topk, int mode, int prec,
+                               int64_t* argmin, int32_t* top_idx, float* top_w, float* top_d,
+                               float* row_min, float* row_sum, float* PiV, int32_t* stats,
+                               void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DVM_CHECK_ARG(X && Y && top_idx && top_d, "dvm_softmap_fwd: X, Y, top_idx, top_d must be non-null");
+    DVM_CHECK_ARG(B > 0 && N > 0 && M > 0, "dvm_softmap_fwd: empty problem (B=%d N=%d M=%d)", B, N, M);
+    DVM_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 256, "dvm_softmap_fwd: C=%d must be a multiple of 4 and <= 256", C);
+    DVM_CHECK_ARG(topk >= 1 && topk <= DVM_TOPK_MAX && topk <= M, "dvm_softmap_fwd: topk=%d must be in [1, min(10, M=%d)]", topk, M);
+    DVM_CHECK_ARG(alpha >= 0.f && isfinite(alpha), "dvm_softmap_fwd: alpha=%f must be finite and >= 0", (double)alpha);
+    DVM_CHECK_ARG(mode == DVM_MODE_HARD || mode == DVM_MODE_SOFT, "dvm_softmap_fwd: bad mode %d", mode);
+    DVM_CHECK_ARG(prec == DVM_PREC_FP32 || prec == DVM_PREC_F16 || prec == DVM_PREC_BF16, "dvm_softmap_fwd: bad prec %d", prec);
+    DVM_CHECK_ARG((V == nullptr) == (Dv == 0) || PiV == nullptr, "dvm_softmap_fwd: V/Dv mismatch");
+    DVM_CHECK_ARG((long long)B * N < 0x7fffffffLL && (long long)B * M < 0x7fffffffLL, "dvm_softmap_fwd: too many rows");
+    const bool soft = mode == DVM_MODE_SOFT;
+    DVM_CHECK_ARG(!soft || top_w, "dvm_softmap_fwd: soft mode needs top_w");
+
+    CandBuffers simt{}, tc{};
+    int* flag_list; int* sfb; float* err_x; float* err_ymax; void* tws; size_t tws_bytes;
+    const size_t need = softmap_ws_layout(ws, ws_bytes, B, N, M, C, prec, &simt, &tc, &flag_list, &sfb,
+                                          &err_x, &err_ymax, &tws, &tws_bytes);
+    if (!ws || need > ws_bytes) {
+        set_error("dvm_softmap_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
+        return DVM_ERR_WORKSPACE;
+    }
+    int* st_out = stats ? stats : sfb;
+    DVM_CUDA(cudaMemsetAsync(st_out, 0, 4 * sizeof(int), st));
+
+    FinalizeArgs fa{};
+    fa.X = X; fa.Y = Y; fa.V = V; fa.B = B; fa.N = N; fa.M = M; fa.C = C; fa.Dv = Dv; fa.topk = topk; fa.alpha = alpha;
+    fa.argmin = argmin; fa.top_idx = top_idx; fa.top_w = top_w; fa.top_d = top_d;
+    fa.row_min = row_min; fa.row_sum = row_sum; fa.PiV = PiV;
+    const int rows = B * N;
+    int rc;
+    if (prec == DVM_PREC_FP32) {
+        if ((rc = launch_cand_simt(X, Y, B, N, M, C, alpha, soft, nullptr, nullptr, rows, simt, st))) return rc;
+        fa.cb = simt; fa.rel_bound = 1e-5f; fa.tie_count = st_out + 1;
+        return launch_finalize(fa, soft, rows, st);
+    }
+    if ((rc = launch_cand_tc(X, Y, B, N, M, C, alpha, soft, prec, tc, err_x, err_ymax, tws, tws_bytes, st))) return rc;
+    fa.cb = tc; fa.rel_bound = 2e-5f; fa.err_x = err_x; fa.err_ymax = err_ymax;
+    fa.flag_list = flag_list; fa.flag_count = st_out;
+    if ((rc = launch_finalize(fa, soft, rows, st))) return rc;
+    // fp32 recomputation of the uncertified rows (count lives on the device: no host sync)
+    if ((rc = launch_cand_simt(X, Y, B, N, M, C, alpha, soft, flag_list, st_out, rows, simt, st))) return rc;
+    fa.cb = simt; fa.rel_bound = 1e-5f; fa.err_x = nullptr; fa.err_ymax = nullptr;
+    fa.row_list = flag_list; fa.row_count = st_out; fa.flag_list = nullptr; fa.flag_count = nullptr; fa.tie_count = st_out + 1;
+    return launch_finalize(fa, soft, rows, st);
+}

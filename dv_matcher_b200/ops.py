@@ -1,0 +1,270 @@
+"""Functional (non-autograd) wrappers: one Python function per C entry point of libdvm_b200.
+
+Each takes/returns torch CUDA tensors, allocates the outputs, fetches scratch from the grow-only
+workspace cache, launches on torch's current stream and raises RuntimeError on a non-zero code.
+"""
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from ._lib import check, f32c, ptr, require_device, stream_ptr
+
+SoftMapOut = namedtuple("SoftMapOut", "argmin top_idx top_w top_d row_min row_sum piv stats")
+
+DEFAULT_PREC = "f16"
+
+
+def softmap_fwd(x, y, v=None, alpha=100.0, topk=10, soft=True, prec=None, want_stats=False):
+    """Fused similarity -> softmax -> top-k -> Pi.V -> arg-min (dvm_softmap_fwd).
+
+    x [B,N,C], y [B,M,C], v [B,M,Dv] or None.  Returns SoftMapOut (argmin i64 [B,N]; top_idx i32,
+    top_w, top_d [B,N,topk]; row_min, row_sum [B,N]; piv [B,N,Dv] or None; stats i32[4] or None).
+    """
+    lib = _lib.load()
+    x, y = f32c(x), f32c(y)
+    require_device(x)
+    B, N, C = x.shape
+    M = y.shape[1]
+    if y.shape[0] != B or y.shape[2] != C:
+        raise RuntimeError(f"softmap_fwd: shape mismatch x{tuple(x.shape)} y{tuple(y.shape)}")
+    prec_i = _lib.PREC[prec or DEFAULT_PREC]
+    dev = x.device
+    Dv = 0
+    if v is not None:
+        v = f32c(v)
+        Dv = v.shape[-1]
+    argmin = torch.empty(B, N, dtype=torch.int64, device=dev)
+    top_idx = torch.empty(B, N, topk, dtype=torch.int32, device=dev)
+    top_d = torch.empty(B, N, topk, dtype=torch.float32, device=dev)
+    top_w = torch.empty(B, N, topk, dtype=torch.float32, device=dev) if soft else None
+    row_min = torch.empty(B, N, dtype=torch.float32, device=dev)
+    row_sum = torch.empty(B, N, dtype=torch.float32, device=dev) if soft else None
+    piv = torch.empty(B, N, Dv, dtype=torch.float32, device=dev) if (soft and v is not None) else None
+    stats = torch.empty(4, dtype=torch.int32, device=dev) if want_stats else None
+    nbytes = lib.dvm_softmap_workspace_bytes(B, N, M, C, prec_i)
+    ws = _lib.workspace.get(nbytes, dev, "softmap")
+    rc = lib.dvm_softmap_fwd(ptr(x), ptr(y), ptr(v) if piv is not None else None, B, N, M, C, Dv if piv is not None else 0,
+                             float(alpha), int(topk), _lib.MODE_SOFT if soft else _lib.MODE_HARD, prec_i,
+                             ptr(argmin), ptr(top_idx), ptr(top_w), ptr(top_d), ptr(row_min), ptr(row_sum), ptr(piv), ptr(stats),
+                             ptr(ws), ws.numel(), stream_ptr())
+    check(rc, "dvm_softmap_fwd")
+    return SoftMapOut(argmin, top_idx, top_w, top_d, row_min, row_sum, piv, stats)
+
+
+def softmap_bwd(x, y, alpha, out, d_w):
+    """Gradient of the kept top-k weights w.r.t. x and y (dvm_softmap_bwd). Returns (dx, dy)."""
+    lib = _lib.load()
+    x, y = f32c(x), f32c(y)
+    B, N, C = x.shape
+    M = y.shape[1]
+    topk = out.top_idx.shape[-1]
+    d_w = f32c(d_w)
+    dx = torch.empty_like(x)
+    dy = torch.zeros_like(y)
+    nbytes = lib.dvm_softmap_bwd_workspace_bytes(B, N, M, C)
+    ws = _lib.workspace.get(nbytes, x.device, "softmap_bwd")
+    rc = lib.dvm_softmap_bwd(ptr(x), ptr(y), B, N, M, C, float(alpha), topk,
+                             ptr(out.top_idx), ptr(out.top_w), ptr(out.top_d), ptr(out.row_min), ptr(out.row_sum), ptr(d_w),
+                             ptr(dx), ptr(dy), ptr(ws), ws.numel(), stream_ptr())
+    check(rc, "dvm_softmap_bwd")
+    return dx, dy
+
+
+def sparse_transfer_fwd(idx, w, y):
+    """out[b,i,:] = sum_k w[b,i,k] y[b, idx[b,i,k], :]  (y [B,M,D])."""
+    lib = _lib.load()
+    y = f32c(y)
+    require_device(y)
+    B, N, K = idx.shape
+    M, D = y.shape[1], y.shape[2]
+    out = torch.empty(B, N, D, dtype=torch.float32, device=y.device)
+    check(lib.dvm_sparse_transfer_fwd(ptr(idx), ptr(w), ptr(y), B, N, M, K, D, ptr(out), stream_ptr()), "dvm_sparse_transfer_fwd")
+    return out
+
+
+def sparse_transfer_bwd(idx, w, y, d_out, need_dw=True, need_dy=True):
+    lib = _lib.load()
+    y, d_out = f32c(y), f32c(d_out)
+    B, N, K = idx.shape
+    M, D = y.shape[1], y.shape[2]
+    dw = torch.empty(B, N, K, dtype=torch.float32, device=y.device) if need_dw else None
+    dy = torch.zeros_like(y) if need_dy else None
+    check(lib.dvm_sparse_transfer_bwd(ptr(idx), ptr(w), ptr(y), ptr(d_out), B, N, M, K, D, ptr(dw), ptr(dy), stream_ptr()),
+          "dvm_sparse_transfer_bwd")
+    return dw, dy
+
+
+def knn3(q, r, k, f64=False, want_d2=False, idx_dtype=torch.int64):
+    """Exact brute-force k-NN on 3-D points: idx [B,N,k] (+ squared distances)."""
+    lib = _lib.load()
+    q, r = f32c(q), f32c(r)
+    require_device(q)
+    B, N, _ = q.shape
+    M = r.shape[1]
+    if q.shape[-1] != 3 or r.shape[-1] != 3 or r.shape[0] != B:
+        raise RuntimeError(f"knn3: expected [B,N,3] / [B,M,3], got {tuple(q.shape)} / {tuple(r.shape)}")
+    idx = torch.empty(B, N, k, dtype=idx_dtype, device=q.device)
+    d2 = torch.empty(B, N, k, dtype=torch.float64 if f64 else torch.float32, device=q.device) if want_d2 else None
+    i64 = ptr(idx) if idx_dtype == torch.int64 else None
+    i32 = ptr(idx) if idx_dtype == torch.int32 else None
+    check(lib.dvm_knn3(ptr(q), ptr(r), B, N, M, int(k), int(bool(f64)), i64, i32,
+                       ptr(d2) if (want_d2 and not f64) else None, ptr(d2) if (want_d2 and f64) else None, stream_ptr()), "dvm_knn3")
+    return (idx, d2) if want_d2 else idx
+
+
+def chamfer_fwd(a, b):
+    lib = _lib.load()
+    a, b = f32c(a), f32c(b)
+    require_device(a)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    dev = a.device
+    d1 = torch.empty(B, N, dtype=torch.float32, device=dev)
+    d2 = torch.empty(B, M, dtype=torch.float32, device=dev)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
+    i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
+    check(lib.dvm_chamfer_fwd(ptr(a), ptr(b), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), stream_ptr()), "dvm_chamfer_fwd")
+    return d1, d2, i1, i2
+
+
+def chamfer_bwd(a, b, i1, i2, g1, g2):
+    lib = _lib.load()
+    a, b, g1, g2 = f32c(a), f32c(b), f32c(g1), f32c(g2)
+    B, N, _ = a.shape
+    M = b.shape[1]
+    da = torch.empty_like(a)
+    db = torch.empty_like(b)
+    check(lib.dvm_chamfer_bwd(ptr(a), ptr(b), ptr(i1), ptr(i2), ptr(g1), ptr(g2), B, N, M, ptr(da), ptr(db), stream_ptr()), "dvm_chamfer_bwd")
+    return da, db
+
+
+def fps(xyz, k, start):
+    """Farthest point sampling with injected start indices: xyz [B,N,3], start i64 [B] -> i64 [B,k]."""
+    lib = _lib.load()
+    xyz = f32c(xyz)
+    require_device(xyz)
+    B, N, _ = xyz.shape
+    start = start.to(device=xyz.device, dtype=torch.int64).contiguous()
+    out = torch.empty(B, k, dtype=torch.int64, device=xyz.device)
+    ws = _lib.workspace.get(lib.dvm_fps_workspace_bytes(B, N), xyz.device, "fps")
+    check(lib.dvm_fps(ptr(xyz), B, N, int(k), ptr(start), ptr(out), ptr(ws), ws.numel(), stream_ptr()), "dvm_fps")
+    return out
+
+
+def graph_weights(xyz, nodes_idx):
+    """Graph tensors for given node lists: (influence i64 [B,N,3], dists, weights, ring i64 [B,K,9], sigma f64 [B])."""
+    lib = _lib.load()
+    xyz = f32c(xyz)
+    require_device(xyz)
+    B, N, _ = xyz.shape
+    K = nodes_idx.shape[1]
+    dev = xyz.device
+    nodes_idx = nodes_idx.to(device=dev, dtype=torch.int64).contiguous()
+    infl = torch.empty(B, N, 3, dtype=torch.int64, device=dev)
+    dists = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    wts = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    ring = torch.empty(B, K, 9, dtype=torch.int64, device=dev)
+    sigma = torch.empty(B, dtype=torch.float64, device=dev)
+    ws = _lib.workspace.get(lib.dvm_graph_workspace_bytes(B, N, K), dev, "graph")
+    check(lib.dvm_graph_weights(ptr(xyz), ptr(nodes_idx), B, N, K, ptr(infl), ptr(dists), ptr(wts), ptr(ring), ptr(sigma),
+                                ptr(ws), ws.numel(), stream_ptr()), "dvm_graph_weights")
+    return infl, dists, wts, ring, sigma
+
+
+def rot6d_fwd(d6):
+    lib = _lib.load()
+    d6 = f32c(d6)
+    require_device(d6)
+    n = d6.numel() // 6
+    R = torch.empty(*d6.shape[:-1], 3, 3, dtype=torch.float32, device=d6.device)
+    check(lib.dvm_rot6d_fwd(ptr(d6), n, ptr(R), stream_ptr()), "dvm_rot6d_fwd")
+    return R
+
+
+def rot6d_bwd(d6, dR):
+    lib = _lib.load()
+    d6, dR = f32c(d6), f32c(dR)
+    n = d6.numel() // 6
+    dd6 = torch.empty_like(d6)
+    check(lib.dvm_rot6d_bwd(ptr(d6), ptr(dR), n, ptr(dd6), stream_ptr()), "dvm_rot6d_bwd")
+    return dd6
+
+
+def skin_fwd(xyz, nodes_idx, infl, wts, R, t):
+    lib = _lib.load()
+    xyz, wts, R, t = f32c(xyz), f32c(wts), f32c(R), f32c(t)
+    require_device(xyz)
+    B, N, _ = xyz.shape
+    K = nodes_idx.shape[1]
+    out = torch.empty_like(xyz)
+    check(lib.dvm_skin_fwd(ptr(xyz), ptr(nodes_idx), ptr(infl), ptr(wts), ptr(R), ptr(t), B, N, K, ptr(out), stream_ptr()), "dvm_skin_fwd")
+    return out
+
+
+def skin_bwd(xyz, nodes_idx, infl, wts, d_out):
+    lib = _lib.load()
+    xyz, wts, d_out = f32c(xyz), f32c(wts), f32c(d_out)
+    B, N, _ = xyz.shape
+    K = nodes_idx.shape[1]
+    dR = torch.empty(B, K, 3, 3, dtype=torch.float32, device=xyz.device)
+    dt = torch.empty(B, K, 3, dtype=torch.float32, device=xyz.device)
+    check(lib.dvm_skin_bwd(ptr(xyz), ptr(nodes_idx), ptr(infl), ptr(wts), ptr(d_out), B, N, K, ptr(dR), ptr(dt), stream_ptr()), "dvm_skin_bwd")
+    return dR, dt
+
+
+def arap_fwd(xyz, nodes_idx, ring, R, t):
+    lib = _lib.load()
+    xyz, R, t = f32c(xyz), f32c(R), f32c(t)
+    require_device(xyz)
+    B, N, _ = xyz.shape
+    K, rk = ring.shape[1], ring.shape[2]
+    arap = torch.empty(B, dtype=torch.float32, device=xyz.device)
+    sr = torch.empty(B, dtype=torch.float32, device=xyz.device)
+    ws = _lib.workspace.get(lib.dvm_arap_workspace_bytes(B, K), xyz.device, "arap")
+    check(lib.dvm_arap_fwd(ptr(xyz), ptr(nodes_idx), ptr(ring), ptr(R), ptr(t), B, N, K, rk, ptr(arap), ptr(sr),
+                           ptr(ws), ws.numel(), stream_ptr()), "dvm_arap_fwd")
+    return arap, sr
+
+
+def arap_bwd(xyz, nodes_idx, ring, R, t, g_arap, dR, dt):
+    """Accumulates g_arap[b] * d arap/d(R,t) into dR, dt (in place)."""
+    lib = _lib.load()
+    xyz, R, t, g_arap = f32c(xyz), f32c(R), f32c(t), f32c(g_arap)
+    B, N, _ = xyz.shape
+    K, rk = ring.shape[1], ring.shape[2]
+    check(lib.dvm_arap_bwd(ptr(xyz), ptr(nodes_idx), ptr(ring), ptr(R), ptr(t), ptr(g_arap), B, N, K, rk, ptr(dR), ptr(dt), stream_ptr()),
+          "dvm_arap_bwd")
+    return dR, dt
+
+
+def gather_conv_fwd(feat, idx, weight, bias):
+    lib = _lib.load()
+    feat = f32c(feat)
+    require_device(feat)
+    B, N, C = feat.shape
+    k = idx.shape[-1]
+    rows = idx.shape[1]
+    if rows != N:
+        raise RuntimeError("gather_conv_fwd: idx must be [B,N,k] over the same cloud")
+    idx = idx.to(torch.int64).contiguous()
+    w = f32c(weight.reshape(-1))
+    b = f32c(bias.reshape(-1)) if bias is not None else None
+    out = torch.empty(B, N, C, dtype=torch.float32, device=feat.device)
+    check(lib.dvm_gather_conv_fwd(ptr(feat), ptr(idx), ptr(w), ptr(b), B, N, C, k, ptr(out), stream_ptr()), "dvm_gather_conv_fwd")
+    return out
+
+
+def gather_conv_bwd(feat, idx, weight, d_out):
+    lib = _lib.load()
+    feat, d_out = f32c(feat), f32c(d_out)
+    B, N, C = feat.shape
+    k = idx.shape[-1]
+    idx = idx.to(torch.int64).contiguous()
+    w = f32c(weight.reshape(-1))
+    d_feat = torch.zeros_like(feat)
+    d_w = torch.zeros(k, dtype=torch.float32, device=feat.device)
+    d_b = torch.zeros(1, dtype=torch.float32, device=feat.device)
+    check(lib.dvm_gather_conv_bwd(ptr(feat), ptr(idx), ptr(w), ptr(d_out), B, N, C, k, ptr(d_feat), ptr(d_w), ptr(d_b), stream_ptr()),
+          "dvm_gather_conv_bwd")
+    return d_feat, d_w, d_b

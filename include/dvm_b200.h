@@ -1,0 +1,167 @@
+/*
+ * dvm_b200.h -- C ABI of libdvm_b200.so: the B200 (sm_100a) hot path of DV-Matcher's dense
+ * correspondence + deformation pipeline.
+ *
+ * Conventions (every entry point):
+ *   - all data pointers are DEVICE pointers owned by the caller (PyTorch), contiguous, row-major;
+ *   - `stream` is a cudaStream_t passed as void*; work is only enqueued, never synchronised;
+ *   - no allocation inside: scratch comes from the caller (`ws`, sized by *_workspace_bytes);
+ *   - return value: 0 on success, a positive cudaError_t, or a negative DVM_ERR_* argument code;
+ *     dvm_last_error_string() describes the last failure on the calling thread;
+ *   - thread-safe per stream (no global mutable state besides cached function attributes).
+ *
+ * Each entry point cites the reference (rqhuang88/DV-Matcher) interface it replaces.
+ */
+#ifndef DVM_B200_H
+#define DVM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVM_VERSION 100
+
+#define DVM_ERR_INVALID_ARG   (-1)
+#define DVM_ERR_WORKSPACE     (-2)
+#define DVM_ERR_UNSUPPORTED   (-3)
+#define DVM_ERR_DEVICE        (-4)
+
+/* similarity precision of dvm_softmap_fwd's candidate pass (final top-k distances are always
+ * re-scored exactly in fp32 from the fp32 inputs, whatever the candidate pass used) */
+#define DVM_PREC_FP32   0   /* CUDA-core fp32 direct differences (exact form, parity mode)        */
+#define DVM_PREC_F16    1   /* tcgen05 kind::f16, fp16 operands, fp32 accumulation in TMEM       */
+#define DVM_PREC_BF16   2   /* tcgen05 kind::f16, bf16 operands, fp32 accumulation in TMEM       */
+
+#define DVM_MODE_HARD   0   /* arg-min / top-k only (knnsearch_t)                                */
+#define DVM_MODE_SOFT   1   /* + row softmax statistics and top-k weights (knnsearch_t_grad+topk_pi) */
+
+#define DVM_TOPK_MAX    10  /* models/loss.py:1340 hard-codes k = 10                             */
+#define DVM_KNN_MAX     16
+
+int         dvm_version(void);
+const char* dvm_last_error_string(void);
+/* 0 if the current device is compute capability 10.x, DVM_ERR_DEVICE otherwise */
+int         dvm_device_check(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long   dvm_launch_count(void);
+/* CUDA-event brackets around every launch of the dominant kernel (the similarity candidate pass of
+ * dvm_softmap_fwd) on its own stream: enable(1) resets and starts recording, read() synchronises the
+ * recorded events and returns the summed duration and the number of launches bracketed. */
+int         dvm_profile_enable(int on);
+int         dvm_profile_read(double* total_ms, int* brackets);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused similarity -> row softmax -> top-k soft map -> Pi.V -> arg-min, never materialising N x M.
+ * Replaces, in one call:  knnsearch_t        models/loss.py:91-95   (argmin, int64, 0-based)
+ *                         knnsearch_t_grad   models/loss.py:110-114 (softmax(-alpha*cdist))
+ *                         topk_pi            models/loss.py:1339-1347 (top-10, un-renormalised)
+ *                         Pi_12 @ verts2     models/loss.py:1408-1409
+ * X[B,N,C], Y[B,M,C], V[B,M,Dv] (may be NULL with Dv=0), fp32.  C % 4 == 0, C <= 256, topk <= 10 <= M.
+ * Outputs (any may be NULL except top_idx/top_d):
+ *   argmin  int64[B,N]      top_idx int32[B,N,topk] (ascending distance; ties -> lower index)
+ *   top_w   f32[B,N,topk]   top_d   f32[B,N,topk] (exact fp32 Euclidean distances)
+ *   row_min f32[B,N] (= d of the nearest column)   row_sum f32[B,N] (= sum_j exp(-alpha (d_j - row_min)))
+ *   PiV     f32[B,N,Dv]
+ *   stats   int32[4]: [0] rows whose top-k the low-precision candidate pass could not certify and
+ *                     that were recomputed by the fp32 pass, [1..3] reserved
+ * ------------------------------------------------------------------------------------------ */
+size_t dvm_softmap_workspace_bytes(int B, int N, int M, int C, int prec);
+int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
+                    int B, int N, int M, int C, int Dv, float alpha, int topk, int mode, int prec,
+                    int64_t* argmin, int32_t* top_idx, float* top_w, float* top_d,
+                    float* row_min, float* row_sum, float* PiV, int32_t* stats,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of the soft map w.r.t. the features (autograd of models/loss.py:110-114 + 1339-1347).
+ * dW[B,N,topk] is the gradient w.r.t. the kept (un-renormalised) weights; produces dX[B,N,C] and
+ * ACCUMULATES into dY[B,M,C] (caller zeroes it).  Uses the saved top_idx/top_w/top_d/row_min/row_sum. */
+size_t dvm_softmap_bwd_workspace_bytes(int B, int N, int M, int C);
+int dvm_softmap_bwd(const float* X, const float* Y, int B, int N, int M, int C, float alpha, int topk,
+                    const int32_t* top_idx, const float* top_w, const float* top_d,
+                    const float* row_min, const float* row_sum, const float* dW,
+                    float* dX, float* dY, void* ws, size_t ws_bytes, void* stream);
+
+/* 10-sparse transfers Pi @ Y for any row width D: torch.matmul(Pi_12, feat2) models/model.py:471,
+ * einsum('bij,bjkm->bikm') models/loss.py:1237 (with Y viewed as [B,M,k*m]).
+ * out[b,i,:] = sum_k w[b,i,k] * Y[b, idx[b,i,k], :].   bwd: dW = <dOut, Y[idx]>, dY += w * dOut. */
+int dvm_sparse_transfer_fwd(const int32_t* idx, const float* w, const float* Y,
+                            int B, int N, int M, int K, int D, float* out, void* stream);
+int dvm_sparse_transfer_bwd(const int32_t* idx, const float* w, const float* Y, const float* dOut,
+                            int B, int N, int M, int K, int D, float* dW, float* dY, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Brute-force k-NN on 3-D points with the exact direct-difference squared distance
+ * ((dx*dx + dy*dy) + dz*dz, no FMA contraction), ascending, ties -> lower index.
+ * Replaces knn_grad(x,y,k) models/loss.py:97-101 / deform.py:24-28 (k=10 on xyz) and the two SciPy
+ * KD-tree queries of lib/deformation_graph_point.py:181-191 (use_f64=1 evaluates in fp64 like SciPy).
+ * Q[B,N,3], R[B,M,3] -> idx int64[B,N,k] (or idx32 int32, either may be NULL), d2 f32[B,N,k] (NULL ok;
+ * with use_f64 the squared distance is rounded to fp32 on output, d2_f64 receives the fp64 value).
+ * ------------------------------------------------------------------------------------------ */
+int dvm_knn3(const float* Q, const float* R, int B, int N, int M, int k, int use_f64,
+             int64_t* idx, int32_t* idx32, float* d2, double* d2_f64, void* stream);
+
+/* chamfer_3DDist forward/backward (ThibaultGROUEIX/ChamferDistancePytorch chamfer3D, call sites
+ * models/loss.py:1099,1223 and 750,874): squared distances, int32 arg-mins, both directions. */
+int dvm_chamfer_fwd(const float* a, const float* b, int B, int N, int M,
+                    float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* stream);
+/* da[B,N,3], db[B,M,3] are OVERWRITTEN. */
+int dvm_chamfer_bwd(const float* a, const float* b, const int32_t* idx1, const int32_t* idx2,
+                    const float* g1, const float* g2, int B, int N, int M,
+                    float* da, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Deformation graph.
+ * dvm_fps: farthest_point_sample lib/deformation_graph_point.py:18-33 with the random start index
+ *   injected (start[B] int64): distance init 1e10, masked min update, first-index arg-max, unfused
+ *   fp32 arithmetic -> node lists bit-identical to the reference.  xyz[B,N,3] -> out int64[B,K].
+ * ------------------------------------------------------------------------------------------ */
+size_t dvm_fps_workspace_bytes(int B, int N);
+int dvm_fps(const float* xyz, int B, int N, int K, const int64_t* start, int64_t* out,
+            void* ws, size_t ws_bytes, void* stream);
+
+/* construct_graph_euclidean lib/deformation_graph_point.py:177-201 minus node selection:
+ * given nodes_idx[B,K] (vertex indices) computes
+ *   influence int64[B,N,3]  3 nearest nodes per vertex (node index space), dists f32[B,N,3],
+ *   weights   f32[B,N,3]    exp(-d^2 / 2 sigma^2) row-normalised,
+ *   ring      int64[B,K,9]  9-NN node ring incl. self (fp64 evaluation, as SciPy),
+ *   sigma     f64[B]        20 * mean distance to the nearest other vertex. */
+size_t dvm_graph_workspace_bytes(int B, int N, int K);
+int dvm_graph_weights(const float* xyz, const int64_t* nodes_idx, int B, int N, int K,
+                      int64_t* influence, float* dists, float* weights, int64_t* ring, double* sigma,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* rotation_6d_to_matrix models/loss.py:39-45: d6[n,6] -> R[n,9] (rows b1,b2,b3); bwd: dR -> dd6. */
+int dvm_rot6d_fwd(const float* d6, int n, float* R, void* stream);
+int dvm_rot6d_bwd(const float* d6, const float* dR, int n, float* dd6, void* stream);
+
+/* DeformationGraph_geod.forward lib/deformation_graph_point.py:233-261, batched over B clouds:
+ * skinning warp  out[b,i] = sum_k w[b,i,k] (R_n (v_i - g_n) + g_n + t_n),  n = influence[b,i,k],
+ * g = xyz[nodes_idx].  R[B,K,9], t[B,K,3].  bwd: dOut[B,N,3] -> dR[B,K,9], dt[B,K,3] (OVERWRITTEN). */
+int dvm_skin_fwd(const float* xyz, const int64_t* nodes_idx, const int64_t* influence, const float* weights,
+                 const float* R, const float* t, int B, int N, int K, float* out, void* stream);
+int dvm_skin_bwd(const float* xyz, const int64_t* nodes_idx, const int64_t* influence, const float* weights,
+                 const float* dOut, int B, int N, int K, float* dR, float* dt, void* stream);
+/* ARAP + rotation smoothness of the same forward: arap[b] = sum_i sum_{j in ring(i)} ||(g_i+t_i) -
+ * (g_j+t_j) - R_i (g_i - g_j)||^2 / K,  sr[b] = mean (R_i - R_j)^2.  Deterministic two-stage reduction.
+ * bwd ACCUMULATES g_arap[b] * d arap / d(R,t) into dR, dt. */
+size_t dvm_arap_workspace_bytes(int B, int K);
+int dvm_arap_fwd(const float* xyz, const int64_t* nodes_idx, const int64_t* ring, const float* R, const float* t,
+                 int B, int N, int K, int ring_k, float* arap, float* sr, void* ws, size_t ws_bytes, void* stream);
+int dvm_arap_bwd(const float* xyz, const int64_t* nodes_idx, const int64_t* ring, const float* R, const float* t,
+                 const float* g_arap, int B, int N, int K, int ring_k, float* dR, float* dt, void* stream);
+
+/* index_points + Conv2d(k->1, 1x1) over the neighbour axis, fused (models/loss.py:1252-1253 feeding
+ * models/model.py:468-469):  out[b,n,c] = bias + sum_s W[s] * feat[b, idx[b,n,s], c].
+ * bwd: dFeat (ACCUMULATED), dW[k], dBias[1] (ACCUMULATED). */
+int dvm_gather_conv_fwd(const float* feat, const int64_t* idx, const float* W, const float* bias,
+                        int B, int N, int C, int k, float* out, void* stream);
+int dvm_gather_conv_bwd(const float* feat, const int64_t* idx, const float* W, const float* dOut,
+                        int B, int N, int C, int k, float* dFeat, float* dW, float* dBias, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVM_B200_H */

@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): arg-min / k-NN / Chamfer / FPS indices bit-exact; soft-map weights,
+transferred coordinates, Chamfer, ARAP and deformed coordinates within 1e-4 relative (fp32).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as og
+from oracle import graph as ogr
+from oracle import maps as om
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # north_star tolerance for fp32 quantities
+
+
+def _ops():
+    from dv_matcher_b200 import ops
+    return ops
+
+
+def _cuda(t):
+    return t.cuda() if torch.is_tensor(t) else torch.as_tensor(t).cuda()
+
+
+def _check_softmap(out, x, y, v, alpha, topk=10, soft=True):
+    """Compare a SoftMapOut with the fp64 arbiter; returns the number of unresolvable (near-tie) rows."""
+    s = om.softmap_sparse(x, y, alpha, k=topk, v=v, dtype=torch.float64)
+    M = y.shape[1]
+    # arg-min: exact wherever the best/second gap is resolvable in fp32
+    am = out.argmin.cpu()
+    res1 = ~om.near_tie_rows(s["gap1"], s["d"][..., 0], rel=2e-6)
+    assert torch.equal(am[res1], s["argmin"][res1])
+    # top-k set + order: exact wherever every adjacent gap (incl. rank k / k+1) is resolvable
+    d = s["d"]
+    adj = torch.cat([d[..., 1:] - d[..., :-1], s["gap"][..., None]], -1).min(-1).values if topk > 1 else s["gap"]
+    res = ~om.near_tie_rows(adj, d[..., -1], rel=2e-6)
+    assert res.float().mean().item() > 0.95
+    assert torch.equal(out.top_idx.cpu().long()[res], s["idx"][res])
+    np.testing.assert_allclose(out.top_d.cpu().numpy()[res.numpy()], d.float().numpy()[res.numpy()], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(out.row_min.cpu().numpy(), d[..., 0].float().numpy(), rtol=2e-6, atol=1e-7)
+    if soft:
+        # weights: error of an entry ~ alpha * (fp32 rounding of d) -- stay inside 1e-4 relative + tiny abs floor
+        w_ref = om.sparse_to_dense(s["idx"], s["w"], M)
+        w_got = om.sparse_to_dense(out.top_idx.cpu().long(), out.top_w.cpu().double(), M)
+        err = ((w_got - w_ref).abs() / w_ref.clamp_min(1e-12))[res]
+        sig = w_ref[res] > 1e-6
+        assert err[sig].max().item() <= RTOL + 4e-6 * alpha, err[sig].max().item()
+        np.testing.assert_allclose(out.row_sum.cpu().numpy(), s["row_sum"].float().numpy(), rtol=RTOL + 4e-6 * alpha)
+        if v is not None:
+            scale = v.abs().max().item()
+            assert (out.piv.cpu().double() - s["piv"]).abs().max().item() <= (RTOL + 4e-6 * alpha) * scale
+    return int((~res).sum())
+
+
+@pytest.mark.parametrize("alpha", [10.0, 50.0, 100.0])
+def test_softmap_fp32_golden_pair(golden_maps, alpha):
+    """Config 2 shape class (N != M, real SCAPE geometry): fp32 path vs fp64 arbiter and reference outputs."""
+    ops = _ops()
+    g = golden_maps
+    x, y = g["feat1"][None], g["feat2"][None]
+    v = torch.from_numpy(g["xyz2"])[None]
+    out = ops.softmap_fwd(_cuda(x), _cuda(y), _cuda(v), alpha=alpha, prec="fp32", want_stats=True)
+    torch.cuda.synchronize()
+    _check_softmap(out, x, y, v, alpha)
+    # hard map equals the unmodified reference's knnsearch_t output bit for bit
+    assert np.array_equal(out.argmin.cpu().numpy()[0], g["T12"].astype(np.int64))
+    # and the transferred vertices agree with the reference within the reference's own GEMM-form noise
+    ref = g[f"verts12_a{int(alpha)}"]
+    assert np.abs(out.piv.cpu().numpy()[0] - ref).max() <= 2.5 * alpha * 2e-4 * np.abs(ref).max()
+
+
+def test_hard_map_both_directions(golden_maps):
+    ops = _ops()
+    g = golden_maps
+    x, y = _cuda(g["feat1"][None]), _cuda(g["feat2"][None])
+    o12 = ops.softmap_fwd(x, y, soft=False, topk=1, prec="fp32")
+    o21 = ops.softmap_fwd(y, x, soft=False, topk=1, prec="fp32")
+    assert np.array_equal(o12.argmin.cpu().numpy()[0], g["T12"].astype(np.int64))
+    assert np.array_equal(o21.argmin.cpu().numpy()[0], g["T21"].astype(np.int64))
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 10, 8), (2, 65, 63, 128), (3, 200, 129, 64), (1, 130, 1000, 256), (2, 77, 300, 4)])
+def test_softmap_fp32_ragged_shapes(shape):
+    """Ragged tile edges, tiny problems, several batch elements, every supported channel-count class."""
+    ops = _ops()
+    B, N, M, C = shape
+    gen = torch.Generator().manual_seed(B * 1000 + N)
+    x = torch.randn(B, N, C, generator=gen)
+    y = torch.randn(B, M, C, generator=gen)
+    v = torch.randn(B, M, 3, generator=gen)
+    out = ops.softmap_fwd(_cuda(x), _cuda(y), _cuda(v), alpha=7.0, prec="fp32")
+    _check_softmap(out, x, y, v, 7.0)
+
+
+def test_softmap_ties_resolve_to_lower_index():
+    ops = _ops()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 40, 32, generator=gen)
+    y = torch.randn(1, 50, 32, generator=gen)
+    y[0, 30] = y[0, 4]          # exact duplicates: distances tie exactly
+    y[0, 41] = y[0, 4]
+    x[0, 0] = y[0, 4] + 0.01
+    out = ops.softmap_fwd(_cuda(x), _cuda(y), alpha=1.0, prec="fp32")
+    idx = out.top_idx.cpu()[0, 0]
+    assert idx[:3].tolist() == [4, 30, 41]
+    assert out.argmin.cpu()[0, 0].item() == 4
+
+
+def test_softmap_argument_errors():
+    ops = _ops()
+    x = torch.randn(1, 8, 12).cuda()
+    with pytest.raises(RuntimeError):
+        ops.softmap_fwd(x, torch.randn(1, 5, 12).cuda(), topk=10)          # M < topk
+    with pytest.raises(RuntimeError):
+        ops.softmap_fwd(torch.randn(1, 8, 6).cuda(), torch.randn(1, 20, 6).cuda())   # C % 4 != 0
+    with pytest.raises(RuntimeError):
+        ops.softmap_fwd(x, torch.randn(1, 20, 12).cuda(), alpha=-1.0)
+    with pytest.raises(RuntimeError):
+        ops.softmap_fwd(x.cpu(), torch.randn(1, 20, 12))                   # no CPU path
+
+
+def test_knn3_bit_exact(golden_graph):
+    ops = _ops()
+    v = torch.from_numpy(golden_graph["xyz"])[None]
+    idx, d2 = ops.knn3(_cuda(v), _cuda(v), 10, want_d2=True)
+    ref_idx, ref_d2 = og.knn_exact(v, v, 10)
+    assert torch.equal(idx.cpu(), ref_idx)
+    assert torch.equal(d2.cpu(), ref_d2)          # unfused arithmetic: bit-identical squared distances
+    # many-query path (1 lane per query) and int32 output, ragged sizes
+    gen = torch.Generator().manual_seed(11)
+    q = torch.rand(2, 1031, 3, generator=gen)
+    r = torch.rand(2, 517, 3, generator=gen)
+    r[1, 100] = r[1, 7]
+    for k in (1, 3, 9, 16):
+        i32 = ops.knn3(_cuda(q), _cuda(r), k, idx_dtype=torch.int32)
+        assert torch.equal(i32.cpu().long(), og.knn_exact(q, r, k)[0])
+    i64, d64 = ops.knn3(_cuda(q), _cuda(r), 9, f64=True, want_d2=True)
+    ref_i, ref_d = og.knn_exact(q, r, 9, torch.float64)
+    assert torch.equal(i64.cpu(), ref_i)
+    np.testing.assert_allclose(d64.cpu().numpy(), ref_d.numpy(), rtol=1e-14)
+
+
+def test_knn3_large_uses_one_lane_path():
+    ops = _ops()
+    gen = torch.Generator().manual_seed(12)
+    q = torch.rand(1, 148 * 2048 + 5, 3, generator=gen)
+    r = torch.rand(1, 300, 3, generator=gen)
+    idx = ops.knn3(_cuda(q), _cuda(r), 3)
+    sel = torch.randperm(q.shape[1], generator=gen)[:4000]
+    assert torch.equal(idx.cpu()[:, sel], og.knn_exact(q[:, sel], r, 3)[0])
+
+
+def test_chamfer_fwd_bwd():
+    ops = _ops()
+    gen = torch.Generator().manual_seed(5)
+    a = torch.randn(2, 1500, 3, generator=gen)
+    b = torch.randn(2, 1111, 3, generator=gen)
+    b[0, 7] = b[0, 3]
+    a[0, 0] = b[0, 3]
+    d1, d2, i1, i2 = ops.chamfer_fwd(_cuda(a), _cuda(b))
+    r1, r2, j1, j2 = og.chamfer_3d(a, b)
+    assert i1.dtype == torch.int32 and torch.equal(i1.cpu(), j1) and torch.equal(i2.cpu(), j2)
+    assert torch.equal(d1.cpu(), r1) and torch.equal(d2.cpu(), r2)
+    g1 = torch.rand(2, 1500, generator=gen)
+    g2 = torch.rand(2, 1111, generator=gen)
+    da, db = ops.chamfer_bwd(_cuda(a), _cuda(b), i1, i2, _cuda(g1), _cuda(g2))
+    ra, rb = og.chamfer_3d_backward(a, b, j1, j2, g1, g2)
+    np.testing.assert_allclose(da.cpu().numpy(), ra.numpy(), rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(db.cpu().numpy(), rb.numpy(), rtol=RTOL, atol=1e-6)
+
+
+def test_fps_bit_identical_to_reference(golden_graph):
+    ops = _ops()
+    g = golden_graph
+    v = torch.from_numpy(g["xyz"])
+    K = v.shape[0] // 2
+    start = torch.tensor([int(g["fps_start"]), 17])
+    both = torch.stack([v, v.flip(0)])
+    out = ops.fps(_cuda(both), K, start)
+    assert np.array_equal(out[0].cpu().numpy(), g["nodes_idx"].astype(np.int64))     # the reference's own node list
+    assert np.array_equal(out[1].cpu().numpy(), ogr.farthest_point_sample(both[1].numpy(), K, 17))
+    # global-memory variant (N > 8192)
+    gen = torch.Generator().manual_seed(2)
+    big = torch.rand(1, 9000, 3, generator=gen)
+    out = ops.fps(_cuda(big), 600, torch.tensor([5]))
+    assert np.array_equal(out[0].cpu().numpy(), ogr.farthest_point_sample(big[0].numpy(), 600, 5))
+
+
+def test_graph_weights(golden_graph):
+    ops = _ops()
+    g = golden_graph
+    v = torch.from_numpy(g["xyz"])
+    nodes = torch.from_numpy(g["nodes_idx"].astype(np.int64))
+    infl, dists, wts, ring, sigma = ops.graph_weights(_cuda(v[None]), _cuda(nodes[None]))
+    ex = ogr.construct_graph_euclidean(v, int(g["fps_start"]), exact=True)
+    assert torch.equal(ring[0].cpu(), ex["one_ring"])
+    assert np.array_equal(ring[0].cpu().numpy(), g["one_ring"].astype(np.int64))     # == SciPy KD-tree in the reference
+    assert torch.equal(infl[0].cpu(), ex["influence"])
+    assert abs(sigma[0].item() - float(g["sigma"])) <= 1e-12 * float(g["sigma"])
+    np.testing.assert_allclose(dists[0].cpu().numpy(), ex["dists"].numpy(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(wts[0].cpu().numpy(), ex["weights"].numpy(), rtol=1e-5, atol=1e-7)
+    # versus the reference's GEMM-form graph: identical except the rows its rounding noise reorders
+    rows = (infl[0].cpu().numpy() != g["influence"]).any(-1)
+    assert rows.sum() <= 25
+    np.testing.assert_allclose(wts[0].cpu().numpy()[~rows], g["weights"][~rows], rtol=RTOL, atol=1e-6)
+
+
+def test_rot6d_skin_arap_vs_reference(golden_graph):
+    ops = _ops()
+    g = golden_graph
+    v = torch.from_numpy(g["xyz"])
+    d9 = torch.from_numpy(g["deform9"])
+    iden = torch.tensor([1, 0, 0, 0, 1, 0], dtype=torch.float32)
+    d6 = (d9[:, 3:] + iden)[None]
+    R = ops.rot6d_fwd(_cuda(d6))
+    np.testing.assert_allclose(R[0].cpu().numpy(), g["R"], rtol=1e-5, atol=1e-6)
+    nodes = _cuda(torch.from_numpy(g["nodes_idx"].astype(np.int64))[None])
+    infl = _cuda(torch.from_numpy(g["influence"].astype(np.int64))[None])
+    ring = _cuda(torch.from_numpy(g["one_ring"].astype(np.int64))[None])
+    wts = _cuda(torch.from_numpy(g["weights"])[None])
+    t = _cuda(d9[None, :, :3])
+    warped = ops.skin_fwd(_cuda(v[None]), nodes, infl, wts, R, t)
+    scale = np.abs(g["warped"]).max()
+    assert np.abs(warped[0].cpu().numpy() - g["warped"]).max() <= RTOL * scale
+    arap, sr = ops.arap_fwd(_cuda(v[None]), nodes, ring, R, t)
+    assert abs(arap[0].item() - float(g["arap"])) <= RTOL * float(g["arap"])
+    assert abs(sr[0].item() - float(g["sr"])) <= RTOL * float(g["sr"])
+
+
+def test_deformation_backward_kernels(golden_graph):
+    ops = _ops()
+    g = golden_graph
+    gen = torch.Generator().manual_seed(21)
+    v = torch.from_numpy(g["xyz"])
+    nodes = torch.from_numpy(g["nodes_idx"].astype(np.int64))
+    infl = torch.from_numpy(g["influence"].astype(np.int64))
+    ring = torch.from_numpy(g["one_ring"].astype(np.int64))
+    wts = torch.from_numpy(g["weights"])
+    d9 = torch.from_numpy(g["deform9"]).clone()
+    iden = torch.tensor([1, 0, 0, 0, 1, 0], dtype=torch.float32)
+    d6 = (d9[:, 3:] + iden).double().requires_grad_(True)
+    t = d9[:, :3].double().requires_grad_(True)
+    R = og.rotation_6d_to_matrix(d6[None])
+    warped, arap, _ = ogr.dg_forward(v.double(), nodes, infl, wts.double(), ring, R, t[None])
+    go = torch.randn(1, v.shape[0], 3, generator=gen).double()
+    ga = 0.37
+    ((warped * go).sum() + ga * arap).backward()
+    # CUDA chain: skin_bwd (+) arap_bwd -> rot6d_bwd
+    Rc = ops.rot6d_fwd(_cuda(d6.detach().float()[None]))
+    dR, dt = ops.skin_bwd(_cuda(v[None]), _cuda(nodes[None]), _cuda(infl[None]), _cuda(wts[None]), _cuda(go.float()))
+    ops.arap_bwd(_cuda(v[None]), _cuda(nodes[None]), _cuda(ring[None]), Rc, _cuda(t.detach().float()[None]),
+                 torch.tensor([ga]).cuda(), dR, dt)
+    dd6 = ops.rot6d_bwd(_cuda(d6.detach().float()[None]), dR)
+    sc6 = d6.grad.abs().max().item()
+    sct = t.grad.abs().max().item()
+    assert (dd6[0].cpu().double() - d6.grad).abs().max().item() <= 2e-4 * sc6
+    assert (dt[0].cpu().double() - t.grad).abs().max().item() <= 2e-4 * sct
+
+
+def test_gather_conv_and_sparse_transfer():
+    ops = _ops()
+    gen = torch.Generator().manual_seed(8)
+    B, N, C, k = 2, 333, 128, 10
+    feat = torch.randn(B, N, C, generator=gen)
+    idx = torch.randint(0, N, (B, N, k), generator=gen)
+    w = torch.randn(k, generator=gen)
+    b = torch.randn(1, generator=gen)
+    out = ops.gather_conv_fwd(_cuda(feat), _cuda(idx), _cuda(w), _cuda(b))
+    ref = (og.index_points(feat, idx) * w[None, None, :, None]).sum(2) + b
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+    go = torch.randn(B, N, C, generator=gen)
+    f2 = feat.clone().double().requires_grad_(True)
+    w2 = w.clone().double().requires_grad_(True)
+    b2 = b.clone().double().requires_grad_(True)
+    (((og.index_points(f2, idx) * w2[None, None, :, None]).sum(2) + b2) * go.double()).sum().backward()
+    df, dw, db = ops.gather_conv_bwd(_cuda(feat), _cuda(idx), _cuda(w), _cuda(go))
+    np.testing.assert_allclose(df.cpu().numpy(), f2.grad.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(dw.cpu().numpy(), w2.grad.numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), b2.grad.numpy(), rtol=1e-4, atol=1e-3)
+    # sparse transfer (Pi @ Y) for D = 3, 30, 128
+    M, K = 257, 10
+    sidx = torch.randint(0, M, (B, N, K), generator=gen).int()
+    sw = torch.rand(B, N, K, generator=gen)
+    for D in (3, 30, 128):
+        Y = torch.randn(B, M, D, generator=gen)
+        dense = om.sparse_to_dense(sidx.long(), sw.double(), M) * 0
+        dense.scatter_add_(-1, sidx.long(), sw.double())           # duplicate indices accumulate
+        ref = dense @ Y.double()
+        got = ops.sparse_transfer_fwd(_cuda(sidx), _cuda(sw), _cuda(Y))
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+        go = torch.randn(B, N, D, generator=gen)
+        dW, dY = ops.sparse_transfer_bwd(_cuda(sidx), _cuda(sw), _cuda(Y), _cuda(go))
+        ref_dW = (go.double()[:, :, None, :] * og.index_points(Y.double(), sidx.long())).sum(-1)
+        ref_dY = torch.zeros(B, M, D, dtype=torch.float64)
+        for bb in range(B):
+            ref_dY[bb].index_add_(0, sidx[bb].reshape(-1).long(), (sw[bb].double()[:, :, None] * go[bb].double()[:, None, :]).reshape(-1, D))
+        np.testing.assert_allclose(dW.cpu().numpy(), ref_dW.numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(dY.cpu().numpy(), ref_dY.numpy(), rtol=1e-4, atol=1e-4)
