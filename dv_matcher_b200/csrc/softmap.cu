@@ -386,6 +386,7 @@ using namespace dvm;
 
 extern "C" size_t dvm_softmap_workspace_bytes(int B, int N, int M, int C, int prec) {
     if (B <= 0 || N <= 0 || M <= 0 || C <= 0) return 0;
+    if (C > 128) prec = DVM_PREC_FP32;
     return softmap_ws_layout(nullptr, 0, B, N, M, C, prec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -406,6 +407,9 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     DVM_CHECK_ARG((long long)B * N < 0x7fffffffLL && (long long)B * M < 0x7fffffffLL, "dvm_softmap_fwd: too many rows");
     const bool soft = mode == DVM_MODE_SOFT;
     DVM_CHECK_ARG(!soft || top_w, "dvm_softmap_fwd: soft mode needs top_w");
+    // the tcgen05 pass keeps a whole K = C operand row block resident in shared memory: C <= 128.
+    // Wider features take the (more precise) fp32 pass.
+    if (C > 128) prec = DVM_PREC_FP32;
 
     CandBuffers simt{}, tc{};
     int* flag_list; int* sfb; float* err_x; float* err_ymax; void* tws; size_t tws_bytes;

@@ -299,3 +299,106 @@ def test_gather_conv_and_sparse_transfer():
             ref_dY[bb].index_add_(0, sidx[bb].reshape(-1).long(), (sw[bb].double()[:, :, None] * go[bb].double()[:, None, :]).reshape(-1, D))
         np.testing.assert_allclose(dW.cpu().numpy(), ref_dW.numpy(), rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(dY.cpu().numpy(), ref_dY.numpy(), rtol=1e-4, atol=1e-4)
+
+
+# --------------------------------------------------------------------------------------------------
+# tcgen05 candidate pass (f16 / bf16 operands, fp32 accumulation in TMEM) + exact fp32 re-scoring
+# --------------------------------------------------------------------------------------------------
+def _report(name, **kv):
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.jsonl", "a") as f:
+        f.write(json.dumps(dict(test=name, **kv)) + "\n")
+
+
+def _tc_errors(out, s, M, v, alpha):
+    """(max relative weight error on significant entries, row_sum rel err, piv err / scale, index mismatches)."""
+    w_ref = om.sparse_to_dense(s["idx"], s["w"], M)
+    w_got = om.sparse_to_dense(out.top_idx.cpu().long(), out.top_w.cpu().double(), M)
+    sig = w_ref > 1e-6
+    werr = ((w_got - w_ref).abs() / w_ref.clamp_min(1e-12))[sig].max().item()
+    rerr = ((out.row_sum.cpu().double() - s["row_sum"]).abs() / s["row_sum"]).max().item()
+    perr = (out.piv.cpu().double() - s["piv"]).abs().max().item() / v.abs().max().item() if v is not None else 0.0
+    mism = int((out.top_idx.cpu().long() != s["idx"]).any(-1).sum())
+    return werr, rerr, perr, mism
+
+
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+@pytest.mark.parametrize("alpha", [10.0, 100.0])
+def test_softmap_tensor_core_golden_pair(golden_maps, prec, alpha):
+    ops = _ops()
+    g = golden_maps
+    x, y = g["feat1"][None], g["feat2"][None]
+    v = torch.from_numpy(g["xyz2"])[None]
+    out = ops.softmap_fwd(_cuda(x), _cuda(y), _cuda(v), alpha=alpha, prec=prec, want_stats=True)
+    ref = ops.softmap_fwd(_cuda(x), _cuda(y), _cuda(v), alpha=alpha, prec="fp32")
+    torch.cuda.synchronize()
+    stats = out.stats.cpu().tolist()
+    # indices and exact distances: identical to the fp32 path bit for bit (certificate + fp32 recomputation)
+    assert torch.equal(out.argmin, ref.argmin)
+    assert np.array_equal(out.argmin.cpu().numpy()[0], g["T12"].astype(np.int64))
+    assert torch.equal(out.top_idx, ref.top_idx)
+    assert torch.equal(out.top_d, ref.top_d)
+    s = om.softmap_sparse(x, y, alpha, v=v, dtype=torch.float64)
+    werr, rerr, perr, mism = _tc_errors(out, s, y.shape[1], v, alpha)
+    _report("tc_golden", prec=prec, alpha=alpha, uncertified_rows=stats[0], ties=stats[1], w_rel_err=werr, rowsum_rel_err=rerr, piv_err=perr)
+    # the weights only feel the 16-bit operands through the softmax mass OUTSIDE the 16 exact candidates
+    bound = 2e-3 if prec == "f16" else 2e-2                      # stated 16-bit bounds (north_star allows a looser one)
+    assert werr <= bound and perr <= bound, (werr, perr)
+
+
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+@pytest.mark.parametrize("shape", [(1, 1, 10, 8), (2, 129, 255, 128), (2, 300, 257, 64), (1, 1000, 1030, 128), (3, 77, 2500, 32)])
+def test_softmap_tensor_core_ragged(prec, shape):
+    ops = _ops()
+    B, N, M, C = shape
+    gen = torch.Generator().manual_seed(B * 1000 + N + 7)
+    x = torch.randn(B, N, C, generator=gen)
+    y = torch.randn(B, M, C, generator=gen)
+    v = torch.randn(B, M, 3, generator=gen)
+    alpha = 5.0
+    out = ops.softmap_fwd(_cuda(x), _cuda(y), _cuda(v), alpha=alpha, prec=prec, want_stats=True)
+    ref = ops.softmap_fwd(_cuda(x), _cuda(y), _cuda(v), alpha=alpha, prec="fp32")
+    assert torch.equal(out.argmin, ref.argmin)
+    assert torch.equal(out.top_idx, ref.top_idx)
+    assert torch.equal(out.top_d, ref.top_d)
+    s = om.softmap_sparse(x, y, alpha, v=v, dtype=torch.float64)
+    werr, rerr, perr, mism = _tc_errors(out, s, M, v, alpha)
+    _report("tc_ragged", prec=prec, shape=list(shape), uncertified_rows=out.stats.cpu().tolist()[0], w_rel_err=werr, rowsum_rel_err=rerr, piv_err=perr)
+    bound = 2e-3 if prec == "f16" else 2e-2      # stated 16-bit bounds on soft weights (DESIGN.md section 5)
+    assert werr <= bound and perr <= bound, (werr, perr)
+
+
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+def test_hard_map_tensor_core(golden_maps, prec):
+    ops = _ops()
+    g = golden_maps
+    x, y = _cuda(g["feat1"][None]), _cuda(g["feat2"][None])
+    o12 = ops.softmap_fwd(x, y, soft=False, topk=1, prec=prec, want_stats=True)
+    o21 = ops.softmap_fwd(y, x, soft=False, topk=1, prec=prec, want_stats=True)
+    assert np.array_equal(o12.argmin.cpu().numpy()[0], g["T12"].astype(np.int64))
+    assert np.array_equal(o21.argmin.cpu().numpy()[0], g["T21"].astype(np.int64))
+    _report("tc_hard", prec=prec, uncertified_12=o12.stats.cpu().tolist()[0], uncertified_21=o21.stats.cpu().tolist()[0])
+
+
+def test_softmap_tensor_core_synthetic_5k():
+    """Config 1 scale (N = M = 4995, C = 128), both feature regimes: f16 path == fp32 path on every index."""
+    ops = _ops()
+    from dv_matcher_b200 import synthetic
+    for regime in ("structured", "unstructured"):
+        d = synthetic.make_batch(1, 4995, 4995, regime=regime)
+        x, y, v = _cuda(d["feat1"]), _cuda(d["feat2"]), _cuda(d["xyz2"])
+        for alpha in (10.0, 100.0):
+            out = ops.softmap_fwd(x, y, v, alpha=alpha, prec="f16", want_stats=True)
+            ref = ops.softmap_fwd(x, y, v, alpha=alpha, prec="fp32")
+            assert torch.equal(out.argmin, ref.argmin)
+            assert torch.equal(out.top_idx, ref.top_idx)
+            perr = (out.piv - ref.piv).abs().max().item() / v.abs().max().item()
+            werr = ((out.top_w - ref.top_w).abs() / ref.top_w.clamp_min(1e-12))[ref.top_w > 1e-6].max().item()
+            _report("tc_5k", regime=regime, alpha=alpha, uncertified_rows=out.stats.cpu().tolist()[0], w_rel_err_vs_fp32=werr, piv_err_vs_fp32=perr)
+            assert perr <= 1e-3 and werr <= 2e-3, (regime, alpha, perr, werr)
+        # spot-check the fp32 path itself against the fp64 arbiter on 256 random rows
+        rows = torch.randperm(4995, generator=torch.Generator().manual_seed(1))[:256]
+        s = om.softmap_sparse(d["feat1"][:, rows], d["feat2"], 100.0, v=d["xyz2"], dtype=torch.float64)
+        assert torch.equal(ref.argmin.cpu()[:, rows], s["argmin"])
+        assert (ref.piv.cpu()[:, rows].double() - s["piv"]).abs().max().item() <= 2e-4 * d["xyz2"].abs().max().item()
