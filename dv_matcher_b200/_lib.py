@@ -43,8 +43,8 @@ SIGNATURES = {
     "dvm_arap_workspace_bytes": (c_size_t, [c_int] * 2),
     "dvm_arap_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "dvm_arap_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 3),
-    "dvm_gather_conv_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 2),
-    "dvm_gather_conv_bwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 4),
+    "dvm_gather_conv_fwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 2),
+    "dvm_gather_conv_bwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 4),
 }
 
 PREC = {"fp32": 0, "f16": 1, "bf16": 2}

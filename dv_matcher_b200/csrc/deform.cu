@@ -213,11 +213,11 @@ constexpr int GC_KMAX = 16;
 
 __global__ void __launch_bounds__(256)
 gather_conv_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ idx, const float* __restrict__ W,
-                       const float* __restrict__ bias, int rows, int N, int C, int k, float* __restrict__ out) {
+                       const float* __restrict__ bias, int rows, int R, int N, int C, int k, float* __restrict__ out) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const int b = row / N;
+    const int b = row / R;
     const float* Fb = feat + (size_t)b * N * C;
     const float bs = bias ? __ldg(bias) : 0.f;
     for (int c = lane * 4; c < C; c += 128) {
@@ -234,7 +234,7 @@ gather_conv_fwd_kernel(const float* __restrict__ feat, const int64_t* __restrict
 
 __global__ void __launch_bounds__(256)
 gather_conv_bwd_kernel(const float* __restrict__ feat, const int64_t* __restrict__ idx, const float* __restrict__ W,
-                       const float* __restrict__ dOut, int rows, int N, int C, int k,
+                       const float* __restrict__ dOut, int rows, int R, int N, int C, int k,
                        float* __restrict__ dFeat, float* __restrict__ dW, float* __restrict__ dBias) {
     __shared__ float s_w[GC_KMAX + 1];
     if (threadIdx.x <= GC_KMAX) s_w[threadIdx.x] = 0.f;
@@ -242,7 +242,7 @@ gather_conv_bwd_kernel(const float* __restrict__ feat, const int64_t* __restrict
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row < rows) {
-        const int b = row / N;
+        const int b = row / R;
         const float* Fb = feat + (size_t)b * N * C;
         float* dFb = dFeat + (size_t)b * N * C;
         float wacc[GC_KMAX];
@@ -390,20 +390,20 @@ extern "C" int dvm_arap_bwd(const float* xyz, const int64_t* nodes_idx, const in
 }
 
 extern "C" int dvm_gather_conv_fwd(const float* feat, const int64_t* idx, const float* W, const float* bias,
-                                   int B, int N, int C, int k, float* out, void* stream) {
+                                   int B, int N, int R, int C, int k, float* out, void* stream) {
     DVM_CHECK_ARG(feat && idx && W && out, "dvm_gather_conv_fwd: null pointer");
-    DVM_CHECK_ARG(B > 0 && N > 0 && C > 0 && C % 4 == 0 && k > 0 && k <= GC_KMAX, "dvm_gather_conv_fwd: bad sizes (C=%d k=%d)", C, k);
-    const int rows = B * N;
-    gather_conv_fwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(feat, idx, W, bias, rows, N, C, k, out);
+    DVM_CHECK_ARG(B > 0 && N > 0 && R > 0 && C > 0 && C % 4 == 0 && k > 0 && k <= GC_KMAX, "dvm_gather_conv_fwd: bad sizes (C=%d k=%d)", C, k);
+    const int rows = B * R;
+    gather_conv_fwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(feat, idx, W, bias, rows, R, N, C, k, out);
     DVM_LAUNCH_CHECK();
     return 0;
 }
 extern "C" int dvm_gather_conv_bwd(const float* feat, const int64_t* idx, const float* W, const float* dOut,
-                                   int B, int N, int C, int k, float* dFeat, float* dW, float* dBias, void* stream) {
+                                   int B, int N, int R, int C, int k, float* dFeat, float* dW, float* dBias, void* stream) {
     DVM_CHECK_ARG(feat && idx && W && dOut && dFeat && dW, "dvm_gather_conv_bwd: null pointer");
-    DVM_CHECK_ARG(B > 0 && N > 0 && C > 0 && C % 4 == 0 && k > 0 && k <= GC_KMAX, "dvm_gather_conv_bwd: bad sizes");
-    const int rows = B * N;
-    gather_conv_bwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(feat, idx, W, dOut, rows, N, C, k, dFeat, dW, dBias);
+    DVM_CHECK_ARG(B > 0 && N > 0 && R > 0 && C > 0 && C % 4 == 0 && k > 0 && k <= GC_KMAX, "dvm_gather_conv_bwd: bad sizes");
+    const int rows = B * R;
+    gather_conv_bwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(feat, idx, W, dOut, rows, R, N, C, k, dFeat, dW, dBias);
     DVM_LAUNCH_CHECK();
     return 0;
 }

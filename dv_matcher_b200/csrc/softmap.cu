@@ -20,6 +20,7 @@ constexpr int SIMT_BN = 64;       // columns per tile
 constexpr int SIMT_CG = 4;        // column groups (threads per row) -> P = 4 partial lists per row
 constexpr int SIMT_CPT = SIMT_BN / SIMT_CG;   // 16 columns per thread per tile
 constexpr int SIMT_THREADS = SIMT_BM * SIMT_CG;
+constexpr int ROWS_EXACT_MAX = 2048;      // up to this many uncertified rows take the one-CTA-per-row kernel
 
 template <bool kSoft>
 __global__ void __launch_bounds__(SIMT_THREADS)
@@ -38,6 +39,7 @@ softmap_cand_simt_kernel(const float* __restrict__ X, const float* __restrict__ 
     int n_rows;
     if (row_list) {
         n_rows = *row_count;
+        if (n_rows <= ROWS_EXACT_MAX) return;                 // few rows: softmap_rows_exact_kernel handles them
         if ((int)blockIdx.x * SIMT_BM >= n_rows) return;
         if (tid < SIMT_BM) {
             const int e = blockIdx.x * SIMT_BM + tid;
@@ -143,6 +145,137 @@ int launch_cand_simt(const float* X, const float* Y, int B, int N, int M, int C,
     if (!row_list) prof_begin(st);
     kern<<<grid, SIMT_THREADS, smem, st>>>(X, Y, N, M, C, row_list, row_count, a2, coa, cb);
     if (!row_list) prof_end(st);
+    DVM_LAUNCH_CHECK();
+    return 0;
+}
+
+// =================================================================================================
+// 1b. exact fp32 pass for a FEW rows (the uncertified rows of the 16-bit pass): one CTA per row, the 256
+//     threads stride over all M columns, so the latency is one column sweep instead of one sweep per
+//     64-row tile.  Two passes over Y: (A) per-thread top-KC -> warp merge -> CTA merge, (B) softmax mass
+//     of the non-candidates relative to the exact row minimum.  Writes partial list 0 of the SIMT buffers.
+// =================================================================================================
+constexpr int RE_THREADS = 256;
+
+__device__ __forceinline__ float row_d2(const float* __restrict__ xs, const float* __restrict__ y, int C) {
+    float acc = 0.f;
+    for (int k = 0; k < C; k += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + k);
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(y + k));
+        float d;
+        d = xv.x - yv.x; acc = fmaf(d, d, acc);
+        d = xv.y - yv.y; acc = fmaf(d, d, acc);
+        d = xv.z - yv.z; acc = fmaf(d, d, acc);
+        d = xv.w - yv.w; acc = fmaf(d, d, acc);
+    }
+    return acc;
+}
+
+template <bool kSoft>
+__global__ void __launch_bounds__(RE_THREADS)
+softmap_rows_exact_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M, int C,
+                          const int* __restrict__ row_list, const int* __restrict__ row_count,
+                          float a2, float cut_over_alpha, CandBuffers cb) {
+    __shared__ __align__(16) float xs[256];
+    __shared__ float s_key[(RE_THREADS / 32) * KC];
+    __shared__ int s_idx[(RE_THREADS / 32) * KC];
+    __shared__ float s_red[RE_THREADS / 32];
+    __shared__ float s_wk; __shared__ int s_wi; __shared__ float s_r;
+    const int n_rows = *row_count;
+    if (n_rows > ROWS_EXACT_MAX || (int)blockIdx.x >= n_rows) return;
+    const int g = row_list[blockIdx.x];
+    const int b = g / N;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int c = tid; c < C; c += RE_THREADS) xs[c] = X[(size_t)g * C + c];
+    __syncthreads();
+    const float* Yb = Y + (size_t)b * M * C;
+
+    // ---- pass A: per-thread sorted top-KC over columns tid, tid+256, ...
+    TopList<KC> list;
+    list.init();
+    for (int j = tid; j < M; j += RE_THREADS) {
+        const float d2 = row_d2(xs, Yb + (size_t)j * C, C);
+        if (d2 < list.worst()) list.push(d2, j);
+    }
+    // warp merge: KC rounds of lexicographic warp-min over the list heads
+    int head = 0;
+    for (int s = 0; s < KC; ++s) {
+        float hk = INFINITY; int hi = 0x7fffffff;
+#pragma unroll
+        for (int t = 0; t < KC; ++t) if (t == head && list.idx[t] >= 0) { hk = list.key[t]; hi = list.idx[t]; }
+        float wk = hk; int wi = hi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, wk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (kv_less(ok, oi, wk, wi)) { wk = ok; wi = oi; }
+        }
+        if (hi == wi && hi != 0x7fffffff) ++head;
+        if (lane == 0) { s_key[wid * KC + s] = wk; s_idx[wid * KC + s] = wi == 0x7fffffff ? -1 : wi; }
+    }
+    __syncthreads();
+    // CTA merge by warp 0: 8 x KC = 128 entries, 4 per lane, KC selection rounds
+    if (wid == 0) {
+        float ek[4]; int ei[4]; bool taken[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ek[q] = s_key[lane + 32 * q]; ei[q] = s_idx[lane + 32 * q]; taken[q] = ei[q] < 0; }
+        const size_t base = (size_t)g * cb.P * KC;
+        float best = INFINITY;
+        for (int s = 0; s < KC; ++s) {
+            float bk = INFINITY; int bi = 0x7fffffff; int bq = -1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (!taken[q] && kv_less(ek[q], ei[q], bk, bi)) { bk = ek[q]; bi = ei[q]; bq = q; }
+            float wk = bk; int wi = bi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ok = __shfl_xor_sync(0xffffffffu, wk, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                if (kv_less(ok, oi, wk, wi)) { wk = ok; wi = oi; }
+            }
+            if (bq >= 0 && bk == wk && bi == wi) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q == bq) taken[q] = true;
+            }
+            if (s == 0) best = wk;
+            if (lane == 0) {
+                cb.key[base + s] = wk;
+                cb.idx[base + s] = wi == 0x7fffffff ? -1 : wi;
+                if (s == KC - 1) { s_wk = wk; s_wi = wi; }
+            }
+        }
+        if (lane == 0) s_r = sqrtf(best);
+        // the other partial lists of this row are empty
+        for (int e = KC + lane; e < cb.P * KC; e += 32) { cb.key[base + e] = INFINITY; cb.idx[base + e] = -1; }
+    }
+    __syncthreads();
+    // ---- pass B: mass of the non-candidates, relative to the exact row minimum
+    float l = 0.f;
+    if (kSoft) {
+        const float wk = s_wk; const int wi = s_wi; const float r = s_r;
+        const float te = r + cut_over_alpha;
+        const float cut2 = te * te;
+        for (int j = tid; j < M; j += RE_THREADS) {
+            const float d2 = row_d2(xs, Yb + (size_t)j * C, C);
+            if (kv_less(wk, wi, d2, j) && d2 < cut2) l += exp2f(-a2 * (sqrtf(d2) - r));
+        }
+        l = warp_sum(l);
+        if (lane == 0) s_red[wid] = l;
+        __syncthreads();
+        if (tid == 0) { l = 0.f; for (int w = 0; w < RE_THREADS / 32; ++w) l += s_red[w]; }
+    }
+    if (tid == 0) {
+        for (int q = 0; q < cb.P; ++q) { cb.l[(size_t)g * cb.P + q] = q == 0 ? l : 0.f; cb.r[(size_t)g * cb.P + q] = q == 0 ? s_r : INFINITY; }
+    }
+}
+
+static int launch_rows_exact(const float* X, const float* Y, int N, int M, int C, float alpha, bool soft,
+                             const int* row_list, const int* row_count, int max_rows, CandBuffers cb, cudaStream_t st) {
+    const int grid = max_rows < ROWS_EXACT_MAX ? max_rows : ROWS_EXACT_MAX;
+    const float a2 = alpha * kLog2e;
+    const float coa = alpha > 0.f ? kExpCut / alpha : INFINITY;
+    if (soft) softmap_rows_exact_kernel<true><<<grid, RE_THREADS, 0, st>>>(X, Y, N, M, C, row_list, row_count, a2, coa, cb);
+    else      softmap_rows_exact_kernel<false><<<grid, RE_THREADS, 0, st>>>(X, Y, N, M, C, row_list, row_count, a2, coa, cb);
     DVM_LAUNCH_CHECK();
     return 0;
 }
@@ -437,7 +570,9 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     fa.cb = tc; fa.rel_bound = 2e-5f; fa.err_x = err_x; fa.err_ymax = err_ymax;
     fa.flag_list = flag_list; fa.flag_count = st_out;
     if ((rc = launch_finalize(fa, soft, rows, st))) return rc;
-    // fp32 recomputation of the uncertified rows (count lives on the device: no host sync)
+    // fp32 recomputation of the uncertified rows (count lives on the device: no host sync): one CTA per row
+    // when there are few of them, the row-tile kernel otherwise (each kernel exits at once in the other case)
+    if ((rc = launch_rows_exact(X, Y, N, M, C, alpha, soft, flag_list, st_out, rows, simt, st))) return rc;
     if ((rc = launch_cand_simt(X, Y, B, N, M, C, alpha, soft, flag_list, st_out, rows, simt, st))) return rc;
     fa.cb = simt; fa.rel_bound = 1e-5f; fa.err_x = nullptr; fa.err_ymax = nullptr;
     fa.row_list = flag_list; fa.row_count = st_out; fa.flag_list = nullptr; fa.flag_count = nullptr; fa.tie_count = st_out + 1;

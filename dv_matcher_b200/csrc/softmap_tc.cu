@@ -138,19 +138,91 @@ struct TcParams {
     float a2, cut_over_alpha;
     uint32_t idesc;
     const float* xx; const float* yy;
+    unsigned* thr_global;        // [B*N] per-row threshold shared by column-split CTAs (null when S == 1)
     CandBuffers cb;
 };
+
+// Epilogue candidate handling (per thread = one row of the tile, one column half):
+//   * the KC best (key, idx) of the row live in REGISTERS as a sorted list;
+//   * columns whose key beats the row threshold are appended, branch-free (predicated STS.64), to a
+//     per-lane buffer in shared memory, slot-major ([slot][lane] -> conflict-free whatever the slots);
+//   * when any lane's buffer is more than 1/3 full the whole warp flushes: every lane inserts ITS OWN
+//     pending entries into its register list at the same time (no divergence in the bootstrap phase,
+//     where all 32 rows are busy), evicted / rejected entries go to the row's softmax mass;
+//   * the threshold of a row is shared between its partial lists -- the two column halves of a CTA via
+//     shared memory, column-split CTAs via atomicMin in global memory -- so the total number of hits per
+//     row stays ~ KC * ln(M) however many partial lists there are.  Any value ever published is the
+//     KC-th best of 16 real columns, hence >= the final merged KC-th best: stale reads are safe.
+constexpr int TC_CAP = 24;                 // buffer slots per lane; flush when any lane holds > 8
+constexpr int TC_CHUNK = 16;               // columns per tcgen05.ld (one flush check per chunk)
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct EpiState {
+    TopList<KC> list;      // keys in the key domain d^2 - |x|^2
+    float thr_list;        // append threshold: min(own KC-th best, thresholds published by the row's other lists)
+    float thr_mass;        // softmax cut-off in the key domain (soft mode): entries in [thr_list, thr_mass) only add mass
+    float r, l;            // running min distance, mass of non-candidate columns relative to r
+    int cnt;               // pending entries in the lane's buffer
+};
+
+template <bool kSoft>
+__device__ __forceinline__ void epi_mass_add(EpiState& st, float key, float xx, float a2) {
+    if (kSoft) {
+        // r is the smallest distance among EVERYTHING counted so far (list or mass): a list that adopted a
+        // tighter threshold from the row's other lists may hold only far entries, so a mass-only column can be
+        // closer than the list head -- rescale instead of evaluating exp2 of a large positive number.
+        const float d = sqrtf(fmaxf(key + xx, 0.f));
+        if (d < st.r) { if (st.l != 0.f) st.l *= exp2f(-a2 * (st.r - d)); st.r = d; }
+        st.l += exp2f(-a2 * (d - st.r));
+    }
+}
+
+// lane-parallel flush of the pending buffers (warp-uniform trip count)
+template <bool kSoft>
+__device__ __forceinline__ void epi_flush(EpiState& st, const float2* buf, int lane, float xx, float a2, float coa) {
+    const int mx = __reduce_max_sync(kFull, st.cnt);
+    for (int e = 0; e < mx; ++e) {
+        if (e < st.cnt) {
+            const float2 kv = buf[e * 32 + lane];
+            const float key = kv.x;
+            if (key < st.list.worst()) {
+                const float ev = st.list.push(key, __float_as_int(kv.y));
+                if (kSoft) {
+                    const float rn = sqrtf(fmaxf(st.list.key[0] + xx, 0.f));
+                    if (rn < st.r) { if (st.l != 0.f) st.l *= exp2f(-a2 * (st.r - rn)); st.r = rn; }
+                    if (ev != INFINITY) epi_mass_add<kSoft>(st, ev, xx, a2);
+                }
+            } else {
+                epi_mass_add<kSoft>(st, key, xx, a2);       // beaten since it was appended: mass only
+            }
+        }
+    }
+    st.cnt = 0;
+    st.thr_list = fminf(st.thr_list, st.list.worst());
+    if (kSoft && st.r != INFINITY) { const float te = st.r + coa; st.thr_mass = te * te - xx; }
+}
 
 template <bool kSoft>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const TcParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment is required by SWIZZLE_128B; the runtime only guarantees 16
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];     // SWIZZLE_128B needs 1024-byte alignment (checked below)
     uint8_t* Xs = smem;
     uint8_t* Ys = Xs + p.KB * TC_X_KB_BYTES;
     float* yy_s = reinterpret_cast<float*>(Ys + TC_NST * p.KB * TC_Y_KB_BYTES);       // [2][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(yy_s + 2 * TC_BN);
+    float2* cand_buf = reinterpret_cast<float2*>(yy_s + 2 * TC_BN);                   // [8 warps][TC_CAP][32] (key, idx)
+    float* thr_sh = reinterpret_cast<float*>(cand_buf + (TC_EPI_THREADS / 32) * TC_CAP * 32);   // [2 halves][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_sh + 2 * TC_BM);
     uint64_t* full = bars;                 // [NST]
     uint64_t* empty = bars + TC_NST;       // [NST]
     uint64_t* tfull = bars + 2 * TC_NST;   // [2]
@@ -166,6 +238,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int ntiles = min(p.tiles_per_split, p.tiles_total - tile0);
 
     if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < TC_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, TC_EPI_THREADS / 32); }
         mbar_init(xfull, 1);
@@ -226,44 +299,73 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's
         const int half = ew >> 2;                          // columns half*128 .. +127 of each tile
         const int etid = threadIdx.x - 64;                 // 0..255
-        const int row = row0 + quarter * 32 + lane;
+        const int rloc = quarter * 32 + lane;              // row inside the CTA tile
+        const int row = row0 + rloc;
         const bool row_ok = row < p.N;
         const float xx = row_ok ? __ldg(p.xx + (size_t)b * p.Npad + row) : 0.f;
-        RowState st;
-        st.init();
-        float thr_key = row_ok ? INFINITY : -INFINITY;     // st.thr - xx; padding rows never visit
+        float2* buf = cand_buf + ew * TC_CAP * 32;
+        volatile float* thr_mine = thr_sh + half * TC_BM + rloc;
+        volatile float* thr_other = thr_sh + (1 - half) * TC_BM + rloc;
+        unsigned* thr_g = p.thr_global ? p.thr_global + (size_t)b * p.N + row : nullptr;    // true-domain d^2 bits
+        *thr_mine = INFINITY;
+        EpiState st;
+        st.list.init();
+        st.thr_list = row_ok ? INFINITY : -INFINITY;       // padding rows never hit
+        st.thr_mass = -INFINITY;                           // no mass-only entries until the running minimum exists
+        st.r = INFINITY; st.l = 0.f; st.cnt = 0;
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int col0 = (tile0 + it) * TC_BN;
             yy_s[acc * TC_BN + etid] = __ldg(p.yy + (size_t)b * p.Mpad + col0 + etid);
+            // pick up thresholds published by the row's other lists -- only once the own list is full, so that
+            // the own running minimum (the reference point of the softmax mass) exists before anything is rejected
+            if (row_ok && st.list.worst() != INFINITY) {
+                float t = *thr_other;
+                if (thr_g) t = fminf(t, __uint_as_float(__ldcg(thr_g)) - xx);
+                st.thr_list = fminf(st.thr_list, t);
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(tfull + acc, aph);
             tc_fence_after();
             const float* yv = yy_s + acc * TC_BN + half * 128;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[32];
-                tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN + half * 128 + c * 32, v);
+            for (int c = 0; c < 128 / TC_CHUNK; ++c) {
+                float v[TC_CHUNK];
+                tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN + half * 128 + c * TC_CHUNK, v);
+                const int cbase = col0 + half * 128 + c * TC_CHUNK;
+                const float thr_hi = kSoft ? fmaxf(st.thr_list, st.thr_mass) : st.thr_list;
+                float key[TC_CHUNK];
+                bool any_mass = false;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float key[8];
-                    const float4 y0 = *reinterpret_cast<const float4*>(yv + c * 32 + g * 8);
-                    const float4 y1 = *reinterpret_cast<const float4*>(yv + c * 32 + g * 8 + 4);
-                    key[0] = fmaf(-2.f, v[g * 8 + 0], y0.x); key[1] = fmaf(-2.f, v[g * 8 + 1], y0.y);
-                    key[2] = fmaf(-2.f, v[g * 8 + 2], y0.z); key[3] = fmaf(-2.f, v[g * 8 + 3], y0.w);
-                    key[4] = fmaf(-2.f, v[g * 8 + 4], y1.x); key[5] = fmaf(-2.f, v[g * 8 + 5], y1.y);
-                    key[6] = fmaf(-2.f, v[g * 8 + 6], y1.z); key[7] = fmaf(-2.f, v[g * 8 + 7], y1.w);
-                    const float m = fminf(fminf(fminf(key[0], key[1]), fminf(key[2], key[3])),
-                                          fminf(fminf(key[4], key[5]), fminf(key[6], key[7])));
-                    if (m < thr_key) {
+                for (int q = 0; q < TC_CHUNK / 4; ++q) {
+                    const float4 y4 = *reinterpret_cast<const float4*>(yv + c * TC_CHUNK + q * 4);
+                    key[q * 4 + 0] = fmaf(-2.f, v[q * 4 + 0], y4.x);
+                    key[q * 4 + 1] = fmaf(-2.f, v[q * 4 + 1], y4.y);
+                    key[q * 4 + 2] = fmaf(-2.f, v[q * 4 + 2], y4.z);
+                    key[q * 4 + 3] = fmaf(-2.f, v[q * 4 + 3], y4.w);
+                }
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            if (key[t] < thr_key) {
-                                row_state_visit<kSoft>(st, key[t] + xx, col0 + half * 128 + c * 32 + g * 8 + t, p.a2, p.cut_over_alpha);
-                                thr_key = st.thr - xx;
-                            }
-                        }
+                for (int t = 0; t < TC_CHUNK; ++t) {
+                    const bool hit = key[t] < st.thr_list;           // predicated, branch-free append
+                    if (hit) buf[st.cnt * 32 + lane] = make_float2(key[t], __int_as_float(cbase + t));
+                    st.cnt += hit ? 1 : 0;
+                    if (kSoft) any_mass |= (!hit) && (key[t] < thr_hi);
+                }
+                if (kSoft) {
+                    if (__any_sync(kFull, any_mass)) {              // rare in the peaked regime
+#pragma unroll
+                        for (int t = 0; t < TC_CHUNK; ++t)
+                            if (key[t] >= st.thr_list && key[t] < thr_hi) epi_mass_add<kSoft>(st, key[t], xx, p.a2);
+                    }
+                }
+                if (__any_sync(kFull, st.cnt > TC_CAP - TC_CHUNK)) {
+                    epi_flush<kSoft>(st, buf, lane, xx, p.a2, p.cut_over_alpha);
+                    if (row_ok) {
+                        const float w = st.list.worst();
+                        *thr_mine = w;
+                        if (w != INFINITY) st.thr_list = fminf(st.thr_list, *thr_other);
+                        if (thr_g && w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(w + xx, 0.f)));
                     }
                 }
             }
@@ -271,12 +373,17 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
         }
+        epi_flush<kSoft>(st, buf, lane, xx, p.a2, p.cut_over_alpha);
         if (row_ok) {
             const size_t g_row = (size_t)b * p.N + row;
             const int pidx = split * 2 + half;
             const size_t base = (g_row * p.cb.P + pidx) * KC;
 #pragma unroll
-            for (int t = 0; t < KC; ++t) { p.cb.key[base + t] = st.list.key[t]; p.cb.idx[base + t] = st.list.idx[t]; }
+            for (int t = 0; t < KC; ++t) {
+                const float k = st.list.key[t];
+                p.cb.key[base + t] = k == INFINITY ? INFINITY : fmaxf(k + xx, 0.f);    // back to the true d^2 domain
+                p.cb.idx[base + t] = st.list.idx[t];
+            }
             p.cb.l[g_row * p.cb.P + pidx] = st.l;
             p.cb.r[g_row * p.cb.P + pidx] = st.r;
         }
@@ -288,6 +395,11 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+__global__ void fill_u32_kernel(unsigned* p, unsigned v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -342,7 +454,8 @@ static int choose_split(int B, int N, int M) {
 int tc_num_partials(int B, int N, int M) { return 2 * choose_split(B, N, M); }
 
 static size_t tc_ws_layout(void* base, size_t cap, int B, int N, int M, int C,
-                           uint16_t** Xh, uint16_t** Yh, float** xx, float** yy, int* Cpad_o, int* Npad_o, int* Mpad_o) {
+                           uint16_t** Xh, uint16_t** Yh, float** xx, float** yy, unsigned** thr_g,
+                           int* Cpad_o, int* Npad_o, int* Mpad_o) {
     const int Cpad = ceil_div(C, TC_KBLK) * TC_KBLK;
     const int Npad = ceil_div(N, TC_BM) * TC_BM;
     const int Mpad = ceil_div(M, TC_BN) * TC_BN;
@@ -351,19 +464,20 @@ static size_t tc_ws_layout(void* base, size_t cap, int B, int N, int M, int C,
     uint16_t* bq = ws.take<uint16_t>((size_t)B * M * Cpad);
     float* c = ws.take<float>((size_t)B * Npad);
     float* d = ws.take<float>((size_t)B * Mpad);
-    if (Xh) *Xh = a; if (Yh) *Yh = bq; if (xx) *xx = c; if (yy) *yy = d;
+    unsigned* tg = ws.take<unsigned>((size_t)B * N);
+    if (Xh) *Xh = a; if (Yh) *Yh = bq; if (xx) *xx = c; if (yy) *yy = d; if (thr_g) *thr_g = tg;
     if (Cpad_o) *Cpad_o = Cpad; if (Npad_o) *Npad_o = Npad; if (Mpad_o) *Mpad_o = Mpad;
     return align_up(ws.off, 256);
 }
 
 size_t tc_workspace_bytes(int B, int N, int M, int C) {
-    return tc_ws_layout(nullptr, 0, B, N, M, C, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return tc_ws_layout(nullptr, 0, B, N, M, C, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, float alpha, bool soft, int prec,
                    CandBuffers cb, float* err_x, float* err_ymax, void* wsp, size_t ws_bytes, cudaStream_t st) {
-    uint16_t *Xh, *Yh; float *xx, *yy; int Cpad, Npad, Mpad;
-    const size_t need = tc_ws_layout(wsp, ws_bytes, B, N, M, C, &Xh, &Yh, &xx, &yy, &Cpad, &Npad, &Mpad);
+    uint16_t *Xh, *Yh; float *xx, *yy; unsigned* thr_g; int Cpad, Npad, Mpad;
+    const size_t need = tc_ws_layout(wsp, ws_bytes, B, N, M, C, &Xh, &Yh, &xx, &yy, &thr_g, &Cpad, &Npad, &Mpad);
     if (!wsp || need > ws_bytes) { set_error("launch_cand_tc: workspace too small"); return DVM_ERR_WORKSPACE; }
     if (B > 65535) { set_error("launch_cand_tc: B=%d too large", B); return DVM_ERR_INVALID_ARG; }
     const bool bf16 = prec == DVM_PREC_BF16;
@@ -401,8 +515,15 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     const uint32_t fmt = bf16 ? 1u : 0u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     p.xx = xx; p.yy = yy; p.cb = cb;
+    p.thr_global = nullptr;
+    if (S > 1) {                                     // +inf bit pattern: 0x7f800000 (byte-wise memset cannot write it)
+        p.thr_global = thr_g;
+        fill_u32_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(thr_g, 0x7f800000u, B * N);
+        DVM_LAUNCH_CHECK();
+    }
 
-    const size_t smem = 1024 + (size_t)p.KB * TC_X_KB_BYTES + (size_t)TC_NST * p.KB * TC_Y_KB_BYTES + 2 * TC_BN * sizeof(float) + 128;
+    const size_t smem = (size_t)p.KB * TC_X_KB_BYTES + (size_t)TC_NST * p.KB * TC_Y_KB_BYTES + 2 * TC_BN * sizeof(float)
+                        + (size_t)(TC_EPI_THREADS / 32) * TC_CAP * 32 * 8 + 2 * TC_BM * sizeof(float) + 128;
     auto kern = soft ? softmap_cand_tc_kernel<true> : softmap_cand_tc_kernel<false>;
     static bool attr_done[2] = {false, false};
     if (!attr_done[soft]) {

@@ -1,0 +1,190 @@
+"""Deformation graph with the reference's call surface, everything on the GPU.
+
+Mirrors lib/deformation_graph_point.py: `farthest_point_sample` (18-33), `DeformationGraph_geod`
+(71-261: `construct_graph_euclidean` 177-201, `forward` 233-261), lib/deformation_graph.py's
+axis-angle `DeformationGraph` (17-116) and the driver `deformation_graph_node`
+(models/loss.py:1325-1337, deform.py:41-53).
+
+What changes underneath: no N x N `cdist` matrix, no device->host copy of it, no SciPy KD-trees, no
+2497-iteration Python FPS loop.  Node selection (dvm_fps), the 3 influencing nodes + Gaussian weights,
+the 9-NN node ring and sigma (dvm_graph_weights) and the warp/ARAP forward+backward (dvm_skin_*,
+dvm_arap_*) are CUDA kernels, batched over the clouds of a batch.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .geometry import rotation_6d_to_matrix  # noqa: F401  (re-exported for callers of the reference's helper)
+
+
+@dataclass
+class BatchedGraph:
+    """Graph tensors of B clouds (same N, K): everything stays on the device."""
+    nodes_idx: torch.Tensor     # int64 [B,K]  vertex index of every node (== `num_nodes_all` of the reference driver)
+    influence: torch.Tensor     # int64 [B,N,3] node index space
+    dists: torch.Tensor         # f32  [B,N,3]
+    weights: torch.Tensor       # f32  [B,N,3]
+    ring: torch.Tensor          # int64 [B,K,9] node index space, self first
+    sigma: torch.Tensor         # f64  [B]
+
+
+def draw_fps_start(B, N):
+    """The reference's RNG draw for the first centroid (lib/deformation_graph_point.py:24):
+    one `torch.randint(0, N, (1,))` on the global CPU generator per cloud, in batch order."""
+    return torch.cat([torch.randint(0, N, (1,), dtype=torch.long) for _ in range(B)])
+
+
+def farthest_point_sample(xyz, npoint, start=None):
+    """lib/deformation_graph_point.py:18-33 for xyz [B,N,3]; `start` [B] injects the first index."""
+    B, N, _ = xyz.shape
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long)
+    return ops.fps(xyz, npoint, start)
+
+
+def build_graphs(verts, start=None):
+    """construct_graph_euclidean for a batch verts [B,N,3] (K = N // 2 nodes, 3 influences, ring of 9)."""
+    B, N, _ = verts.shape
+    if start is None:
+        start = draw_fps_start(B, N)
+    verts = verts.float().contiguous()
+    nodes_idx = ops.fps(verts, N // 2, start)
+    infl, dists, wts, ring, sigma = ops.graph_weights(verts, nodes_idx)
+    return BatchedGraph(nodes_idx, infl, dists, wts, ring, sigma)
+
+
+class _Deform(torch.autograd.Function):
+    """(R [B,K,3,3], t [B,K,3]) -> warped [B,N,3], arap [B], sr [B]; geometry and graph carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, verts, R, t, nodes_idx, infl, wts, ring):
+        verts, R, t = verts.float().contiguous(), R.float().contiguous(), t.float().contiguous()
+        warped = ops.skin_fwd(verts, nodes_idx, infl, wts, R, t)
+        arap, sr = ops.arap_fwd(verts, nodes_idx, ring, R, t)
+        ctx.save_for_backward(verts, R, t, nodes_idx, infl, wts, ring)
+        ctx.mark_non_differentiable(sr)
+        return warped, arap, sr
+
+    @staticmethod
+    def backward(ctx, d_warped, d_arap, _d_sr):
+        verts, R, t, nodes_idx, infl, wts, ring = ctx.saved_tensors
+        dR, dt = ops.skin_bwd(verts, nodes_idx, infl, wts, d_warped.contiguous())
+        ops.arap_bwd(verts, nodes_idx, ring, R, t, d_arap.contiguous(), dR, dt)
+        return None, dR, dt, None, None, None, None
+
+
+def deform_batched(verts, graph, R, t):
+    """Batched DeformationGraph_geod.forward: returns (warped [B,N,3], arap [B], sr [B])."""
+    return _Deform.apply(verts, R, t, graph.nodes_idx, graph.influence, graph.weights, graph.ring)
+
+
+class DeformationGraph_geod(nn.Module):
+    """Per-cloud object with the reference's attributes and methods (lib/deformation_graph_point.py:71)."""
+
+    def __init__(self, radius=0.1, k=3, sampling_strategy="qslim"):
+        super().__init__()
+        self.radius = radius
+        self.k = k
+        self.max_neigh_num = 18
+        self.sampling_strategy = sampling_strategy
+        self.one_ring_neigh = []
+        self.nodes_idx = None
+        self.weights = None
+        self.influence_nodes_idx = []
+        self.dists = []
+        self._graph = None
+
+    def construct_graph_euclidean(self, vertices=None, geod=None, device=None, start=None):
+        """`geod` (the reference's N x N Euclidean matrix) is accepted and ignored: distances are
+        evaluated inside the kernels with the exact direct-difference form."""
+        if self.k != 3:
+            raise NotImplementedError("the reference hard-codes k = 3 influencing nodes")
+        v = torch.as_tensor(vertices).float()
+        if device is None:
+            device = v.device if v.is_cuda else torch.device("cuda")
+        v = v.to(device)[None]
+        g = build_graphs(v, start=None if start is None else torch.as_tensor([int(start)]))
+        self._graph = g
+        self._device_verts = None
+        self.max_neigh_num = 9
+        # reference-visible attributes (numpy int64 where the reference has numpy)
+        self.nodes_idx = g.nodes_idx[0].cpu().numpy()
+        self.nodes = v[0][g.nodes_idx[0]].cpu()
+        self.one_ring_neigh = g.ring[0].cpu().numpy()
+        self.influence_nodes_idx = g.influence[0]
+        self.dists = g.dists[0]
+        self.weights = g.weights[0]
+        self.sigma = g.sigma[0].cpu()
+        return self
+
+    def forward(self, vertices, opt_d_rotations, opt_d_translations):
+        """vertices [N,3], R [1,K,3,3], t [1,K,3] -> ([1,N,3], arap, sr) (lib/deformation_graph_point.py:233-261)."""
+        if self._graph is None:
+            raise RuntimeError("construct_graph_euclidean must be called first")
+        warped, arap, sr = deform_batched(vertices[None], self._graph, opt_d_rotations, opt_d_translations)
+        return warped, arap[0], sr[0]
+
+
+class DeformationGraph(DeformationGraph_geod):
+    """Axis-angle variant (lib/deformation_graph.py:17-116): rotations arrive as [1,K,3] axis-angle."""
+
+    def forward(self, vertices, opt_d_rotations, opt_d_translations):
+        R = batch_rodrigues(opt_d_rotations[0]).unsqueeze(0)
+        return super().forward(vertices, R, opt_d_translations)
+
+
+def batch_rodrigues(axisang):
+    """lib/utils.py:70-112 (angle = ||a + 1e-8||, quaternion, normalised, 3x3); small per-node torch math."""
+    angle = torch.norm(axisang + 1e-8, p=2, dim=1).unsqueeze(-1)
+    n = axisang / angle
+    half = angle * 0.5
+    quat = torch.cat([torch.cos(half), torch.sin(half) * n], dim=1)
+    quat = quat / quat.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+    w2, x2, y2, z2 = w * w, x * x, y * y, z * z
+    wx, wy, wz, xy, xz, yz = w * x, w * y, w * z, x * y, x * z, y * z
+    return torch.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=1).view(-1, 3, 3)
+
+
+def deformation_graph_node(verts1):
+    """Driver of models/loss.py:1325-1337 / deform.py:41-53: returns (num_nodes_all [B,K] float tensor
+    like the reference -- callers apply .long() --, list of per-cloud graph objects)."""
+    B, N, _ = verts1.shape
+    g = build_graphs(verts1)
+    dg_list = []
+    for i in range(B):
+        dg = DeformationGraph_geod()
+        dg._graph = BatchedGraph(g.nodes_idx[i:i + 1], g.influence[i:i + 1], g.dists[i:i + 1], g.weights[i:i + 1],
+                                 g.ring[i:i + 1], g.sigma[i:i + 1])
+        dg.max_neigh_num = 9
+        dg.nodes_idx = _LazyNumpy(g.nodes_idx[i])
+        dg.one_ring_neigh = _LazyNumpy(g.ring[i])
+        dg.influence_nodes_idx = g.influence[i]
+        dg.dists = g.dists[i]
+        dg.weights = g.weights[i]
+        dg.sigma = g.sigma[i]
+        dg_list.append(dg)
+    return g.nodes_idx.to(verts1.dtype if verts1.dtype.is_floating_point else torch.float32), dg_list
+
+
+class _LazyNumpy:
+    """Device tensor that turns into the reference's numpy array only if somebody asks (no sync otherwise)."""
+
+    def __init__(self, t):
+        self._t = t
+        self.shape = tuple(t.shape)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._t.cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, i):
+        return np.asarray(self)[i]

@@ -244,14 +244,12 @@ def gather_conv_fwd(feat, idx, weight, bias):
     require_device(feat)
     B, N, C = feat.shape
     k = idx.shape[-1]
-    rows = idx.shape[1]
-    if rows != N:
-        raise RuntimeError("gather_conv_fwd: idx must be [B,N,k] over the same cloud")
+    R = idx.shape[1]
     idx = idx.to(torch.int64).contiguous()
     w = f32c(weight.reshape(-1))
     b = f32c(bias.reshape(-1)) if bias is not None else None
-    out = torch.empty(B, N, C, dtype=torch.float32, device=feat.device)
-    check(lib.dvm_gather_conv_fwd(ptr(feat), ptr(idx), ptr(w), ptr(b), B, N, C, k, ptr(out), stream_ptr()), "dvm_gather_conv_fwd")
+    out = torch.empty(B, R, C, dtype=torch.float32, device=feat.device)
+    check(lib.dvm_gather_conv_fwd(ptr(feat), ptr(idx), ptr(w), ptr(b), B, N, R, C, k, ptr(out), stream_ptr()), "dvm_gather_conv_fwd")
     return out
 
 
@@ -260,11 +258,12 @@ def gather_conv_bwd(feat, idx, weight, d_out):
     feat, d_out = f32c(feat), f32c(d_out)
     B, N, C = feat.shape
     k = idx.shape[-1]
+    R = idx.shape[1]
     idx = idx.to(torch.int64).contiguous()
     w = f32c(weight.reshape(-1))
     d_feat = torch.zeros_like(feat)
     d_w = torch.zeros(k, dtype=torch.float32, device=feat.device)
     d_b = torch.zeros(1, dtype=torch.float32, device=feat.device)
-    check(lib.dvm_gather_conv_bwd(ptr(feat), ptr(idx), ptr(w), ptr(d_out), B, N, C, k, ptr(d_feat), ptr(d_w), ptr(d_b), stream_ptr()),
+    check(lib.dvm_gather_conv_bwd(ptr(feat), ptr(idx), ptr(w), ptr(d_out), B, N, R, C, k, ptr(d_feat), ptr(d_w), ptr(d_b), stream_ptr()),
           "dvm_gather_conv_bwd")
     return d_feat, d_w, d_b

@@ -154,12 +154,13 @@ int dvm_arap_bwd(const float* xyz, const int64_t* nodes_idx, const int64_t* ring
                  const float* g_arap, int B, int N, int K, int ring_k, float* dR, float* dt, void* stream);
 
 /* index_points + Conv2d(k->1, 1x1) over the neighbour axis, fused (models/loss.py:1252-1253 feeding
- * models/model.py:468-469):  out[b,n,c] = bias + sum_s W[s] * feat[b, idx[b,n,s], c].
+ * models/model.py:468-469):  out[b,r,c] = bias + sum_s W[s] * feat[b, idx[b,r,s], c]  for feat[B,N,C],
+ * idx[B,R,k] (R output rows per cloud: all N vertices, or only the K graph nodes).
  * bwd: dFeat (ACCUMULATED), dW[k], dBias[1] (ACCUMULATED). */
 int dvm_gather_conv_fwd(const float* feat, const int64_t* idx, const float* W, const float* bias,
-                        int B, int N, int C, int k, float* out, void* stream);
+                        int B, int N, int R, int C, int k, float* out, void* stream);
 int dvm_gather_conv_bwd(const float* feat, const int64_t* idx, const float* W, const float* dOut,
-                        int B, int N, int C, int k, float* dFeat, float* dW, float* dBias, void* stream);
+                        int B, int N, int R, int C, int k, float* dFeat, float* dW, float* dBias, void* stream);
 
 #ifdef __cplusplus
 }
