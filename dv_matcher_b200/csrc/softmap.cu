@@ -292,6 +292,8 @@ struct FinalizeArgs {
     CandBuffers cb;
     const int* row_list; const int* row_count;     // optional subset of rows
     const float* err_x; const float* err_ymax;     // candidate-pass distance error bounds (may be null)
+    const float* tc_xx; const float* tc_yymax;     // |x~|^2 per row, max |y~|^2 per batch: scale of the tensor-core
+                                                   // accumulation error of a candidate key (null for the fp32 pass)
     float rel_bound;                               // + rel_bound * d16
     int* flag_list; int* flag_count;               // rows failing the certificate (may be null)
     int* tie_count;                                // counts uncertified rows when flag_list is null
@@ -432,15 +434,22 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
         }
     }
 
-    // ---- certificate: every discarded column has candidate-pass distance >= sqrt(key16)
+    // ---- certificate: every discarded column has candidate-pass key >= key16, i.e. a true distance of at least
+    //      sqrt(key16 - E2) - (|x - x~| + |y - y~|) - rel * d16, E2 = accumulation error of the tensor-core key
     {
         const unsigned m = __ballot_sync(0xffffffffu, rank == a.topk - 1);
         const float dk = m ? __shfl_sync(0xffffffffu, my_d, __ffs(m) - 1) : INFINITY;
-        if (lane == 0 && key16 != INFINITY) {
-            const float d16 = sqrtf(key16);
-            float bound = a.rel_bound * d16;
-            if (a.err_x) bound += a.err_x[g] + a.err_ymax[b];
-            if (!(dk < d16 - bound)) {
+        if (lane == 0) {
+            float bound = 0.f, e2 = 0.f;
+            if (a.err_x) bound = a.err_x[g] + a.err_ymax[b];
+            if (a.tc_xx) e2 = 2e-6f * (a.tc_xx[g] + a.tc_yymax[b]);
+            bool ok;
+            if (key16 == INFINITY) ok = bound < INFINITY;            // every column is in the list (M < KC) unless the
+            else {                                                   // 16-bit conversion overflowed
+                const float d16 = sqrtf(fmaxf(key16 - e2, 0.f));
+                ok = dk < d16 - (bound + a.rel_bound * d16);
+            }
+            if (!ok) {
                 if (a.flag_list) a.flag_list[atomicAdd(a.flag_count, 1)] = g;
                 else if (a.tie_count) atomicAdd(a.tie_count, 1);
             }
@@ -566,7 +575,7 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
         fa.cb = simt; fa.rel_bound = 1e-5f; fa.tie_count = st_out + 1;
         return launch_finalize(fa, soft, rows, st);
     }
-    if ((rc = launch_cand_tc(X, Y, B, N, M, C, alpha, soft, prec, tc, err_x, err_ymax, tws, tws_bytes, st))) return rc;
+    if ((rc = launch_cand_tc(X, Y, B, N, M, C, alpha, soft, prec, tc, err_x, err_ymax, &fa.tc_xx, &fa.tc_yymax, tws, tws_bytes, st))) return rc;
     fa.cb = tc; fa.rel_bound = 2e-5f; fa.err_x = err_x; fa.err_ymax = err_ymax;
     fa.flag_list = flag_list; fa.flag_count = st_out;
     if ((rc = launch_finalize(fa, soft, rows, st))) return rc;
@@ -574,7 +583,7 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     // when there are few of them, the row-tile kernel otherwise (each kernel exits at once in the other case)
     if ((rc = launch_rows_exact(X, Y, N, M, C, alpha, soft, flag_list, st_out, rows, simt, st))) return rc;
     if ((rc = launch_cand_simt(X, Y, B, N, M, C, alpha, soft, flag_list, st_out, rows, simt, st))) return rc;
-    fa.cb = simt; fa.rel_bound = 1e-5f; fa.err_x = nullptr; fa.err_ymax = nullptr;
+    fa.cb = simt; fa.rel_bound = 1e-5f; fa.err_x = nullptr; fa.err_ymax = nullptr; fa.tc_xx = nullptr; fa.tc_yymax = nullptr;
     fa.row_list = flag_list; fa.row_count = st_out; fa.flag_list = nullptr; fa.flag_count = nullptr; fa.tie_count = st_out + 1;
     return launch_finalize(fa, soft, rows, st);
 }

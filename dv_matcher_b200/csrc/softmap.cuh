@@ -19,11 +19,13 @@ int launch_cand_simt(const float* X, const float* Y, int B, int N, int M, int C,
                      const int* row_list, const int* row_count, int max_rows,
                      CandBuffers cb, cudaStream_t st);
 
-// tcgen05 candidate pass (softmap_tc.cu).  Xh/Yh: operands converted to 16-bit with the K extent
-// padded to Cpad (multiple of 64); xx/yy: squared norms of the ROUNDED operands.
+// tcgen05 candidate pass (softmap_tc.cu): operands converted to 16-bit, K padded to a multiple of 64 plus a
+// 16-wide block that folds |y~|^2/2 into the GEMM; candidate keys come back in the true d^2 domain.
 size_t tc_workspace_bytes(int B, int N, int M, int C);
+// xx_out / yymax_out receive device pointers (inside ws) to |x~|^2 per row [B*N] and max |y~|^2 per batch [B].
 int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, float alpha, bool soft, int prec,
-                   CandBuffers cb, float* err_x, float* err_ymax, void* ws, size_t ws_bytes, cudaStream_t st);
+                   CandBuffers cb, float* err_x, float* err_ymax, const float** xx_out, const float** yymax_out,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_num_partials(int B, int N, int M);
 
 }  // namespace dvm
