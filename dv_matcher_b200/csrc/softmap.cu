@@ -125,6 +125,7 @@ softmap_cand_simt_kernel(const float* __restrict__ X, const float* __restrict__ 
         for (int t = 0; t < KC; ++t) { cb.key[base + t] = st.list.key[t]; cb.idx[base + t] = st.list.idx[t]; }
         cb.l[(size_t)g_row * cb.P + cg] = st.l;
         cb.r[(size_t)g_row * cb.P + cg] = st.r;
+        cb.t[(size_t)g_row * cb.P + cg] = INFINITY;
     }
 }
 
@@ -265,7 +266,9 @@ softmap_rows_exact_kernel(const float* __restrict__ X, const float* __restrict__
         if (tid == 0) { l = 0.f; for (int w = 0; w < RE_THREADS / 32; ++w) l += s_red[w]; }
     }
     if (tid == 0) {
-        for (int q = 0; q < cb.P; ++q) { cb.l[(size_t)g * cb.P + q] = q == 0 ? l : 0.f; cb.r[(size_t)g * cb.P + q] = q == 0 ? s_r : INFINITY; }
+        for (int q = 0; q < cb.P; ++q) {
+            cb.l[(size_t)g * cb.P + q] = q == 0 ? l : 0.f; cb.r[(size_t)g * cb.P + q] = q == 0 ? s_r : INFINITY; cb.t[(size_t)g * cb.P + q] = INFINITY;
+        }
     }
 }
 
@@ -296,9 +299,108 @@ struct FinalizeArgs {
                                                    // accumulation error of a candidate key (null for the fp32 pass)
     float rel_bound;                               // + rel_bound * d16
     int* flag_list; int* flag_count;               // rows failing the certificate (may be null)
+    float* flag_thr; float* flag_r;                // per flag slot: squared scan threshold, reference distance (may be null)
     int* tie_count;                                // counts uncertified rows when flag_list is null
     int64_t* argmin; int* top_idx; float* top_w; float* top_d; float* row_min; float* row_sum; float* PiV;
 };
+
+// Exact fp32 re-scoring of up to 32 selected columns of row g (lane s holds sel_idx, -1 = none), ordering
+// ((d^2, idx) lexicographic), weights relative to the exact row minimum, outputs and Pi.V.
+// l_other = softmax mass of every column NOT among the selected ones, relative to distance r_other.
+// Returns dk = exact distance of rank topk-1 (INFINITY if fewer were selected) and dmin.
+template <bool kSoft>
+__device__ __forceinline__ void rescore_emit(const FinalizeArgs& a, int g, int b, int lane, int sel_idx, int n_max,
+                                             float l_other, float r_other, float& dk_out, float& dmin_out) {
+    const float a2 = a.alpha * kLog2e;
+    // d2 = sum_c (x_c - y_c)^2, lane owns channels 4*lane + 128 t, butterfly sum
+    float4 xv[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int c = 4 * lane + 128 * t;
+        xv[t] = (c < a.C) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)g * a.C + c)) : make_float4(0, 0, 0, 0);
+    }
+    float my_d2 = INFINITY; int my_idx = 0x7fffffff;
+    const float* Yb = a.Y + (size_t)b * a.M * a.C;
+    for (int s = 0; s < n_max; ++s) {
+        const int j = __shfl_sync(0xffffffffu, sel_idx, s);
+        if (j < 0) break;                                             // uniform
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int c = 4 * lane + 128 * t;
+            if (c < a.C) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)j * a.C + c));
+                float d;
+                d = xv[t].x - yv.x; acc = fmaf(d, d, acc);
+                d = xv[t].y - yv.y; acc = fmaf(d, d, acc);
+                d = xv[t].z - yv.z; acc = fmaf(d, d, acc);
+                d = xv[t].w - yv.w; acc = fmaf(d, d, acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == s) { my_d2 = acc; my_idx = j; }
+    }
+
+    // ---- rank the exact scores: (d2, idx) lexicographic
+    int rank = 0;
+    for (int s = 0; s < n_max; ++s) {
+        const float od = __shfl_sync(0xffffffffu, my_d2, s);
+        const int oi = __shfl_sync(0xffffffffu, my_idx, s);
+        rank += kv_less(od, oi, my_d2, my_idx) ? 1 : 0;
+    }
+    const bool valid = lane < n_max && my_idx != 0x7fffffff;
+    if (!valid) rank = 99;
+    const float my_d = valid ? sqrtf(my_d2) : INFINITY;
+    float dmin = my_d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+
+    float my_w = 0.f, total = 1.f;
+    if (kSoft) {
+        const float e = valid ? expf(-a.alpha * (my_d - dmin)) : 0.f;
+        total = warp_sum(e);
+        if (l_other != 0.f) total += l_other * exp2f(-a2 * (r_other - dmin));
+        my_w = e / total;
+    }
+
+    if (valid && rank < a.topk) {
+        const size_t o = (size_t)g * a.topk + rank;
+        a.top_idx[o] = my_idx;
+        a.top_d[o] = my_d;
+        if (a.top_w) a.top_w[o] = my_w;
+        if (rank == 0) {
+            if (a.argmin) a.argmin[g] = my_idx;
+            if (a.row_min) a.row_min[g] = my_d;
+            if (a.row_sum) a.row_sum[g] = total;
+        }
+    }
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, rank == a.topk - 1);
+        dk_out = m ? __shfl_sync(0xffffffffu, my_d, __ffs(m) - 1) : INFINITY;
+        dmin_out = dmin;
+    }
+
+    // ---- Pi . V  (10-sparse gather), lanes over the Dv output channels
+    if (kSoft && a.V && a.PiV) {
+        float wk[DVM_TOPK_MAX]; int jk[DVM_TOPK_MAX];
+#pragma unroll
+        for (int k = 0; k < DVM_TOPK_MAX; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, rank == k);
+            const int src = m ? __ffs(m) - 1 : 0;
+            wk[k] = m ? __shfl_sync(0xffffffffu, my_w, src) : 0.f;
+            jk[k] = m ? __shfl_sync(0xffffffffu, my_idx, src) : 0;
+            if (k >= a.topk) wk[k] = 0.f;
+        }
+        const float* Vb = a.V + (size_t)b * a.M * a.Dv;
+        for (int dv = lane; dv < a.Dv; dv += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < DVM_TOPK_MAX; ++k)
+                if (wk[k] != 0.f) acc = fmaf(wk[k], __ldg(Vb + (size_t)jk[k] * a.Dv + dv), acc);
+            a.PiV[(size_t)g * a.Dv + dv] = acc;
+        }
+    }
+}
 
 template <bool kSoft>
 __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(FinalizeArgs a) {
@@ -361,7 +463,13 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
         }
         if (lane == s) { sel_key = wk; sel_idx = wi; }
     }
-    const float key16 = __shfl_sync(0xffffffffu, sel_key, KC - 1);
+    float key16 = __shfl_sync(0xffffffffu, sel_key, KC - 1);
+    {                                                                 // discard bounds of the partial lists
+        float tp = lane < P ? a.cb.t[(size_t)g * P + lane] : INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tp = fminf(tp, __shfl_xor_sync(0xffffffffu, tp, o));
+        key16 = fminf(key16, tp);
+    }
     if (kSoft) {                                                      // listed but not selected: approximate terms
         float t = 0.f;
 #pragma unroll
@@ -370,112 +478,162 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
         l_tot += warp_sum(t);
     }
 
-    // ---- exact re-scoring: d2 = sum_c (x_c - y_c)^2, lane owns channels 4*lane + 128 t, butterfly sum
-    float4 xv[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const int c = 4 * lane + 128 * t;
-        xv[t] = (c < a.C) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)g * a.C + c)) : make_float4(0, 0, 0, 0);
-    }
-    float my_d2 = INFINITY; int my_idx = 0x7fffffff;
-    const float* Yb = a.Y + (size_t)b * a.M * a.C;
-    for (int s = 0; s < KC; ++s) {
-        const int j = __shfl_sync(0xffffffffu, sel_idx, s);
-        if (j < 0) break;                                             // uniform
-        float acc = 0.f;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int c = 4 * lane + 128 * t;
-            if (c < a.C) {
-                const float4 yv = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)j * a.C + c));
-                float d;
-                d = xv[t].x - yv.x; acc = fmaf(d, d, acc);
-                d = xv[t].y - yv.y; acc = fmaf(d, d, acc);
-                d = xv[t].z - yv.z; acc = fmaf(d, d, acc);
-                d = xv[t].w - yv.w; acc = fmaf(d, d, acc);
-            }
-        }
-        acc = warp_sum(acc);
-        if (lane == s) { my_d2 = acc; my_idx = j; }
-    }
-
-    // ---- rank the (<= 16) exact scores: (d2, idx) lexicographic
-    int rank = 0;
-#pragma unroll
-    for (int s = 0; s < KC; ++s) {
-        const float od = __shfl_sync(0xffffffffu, my_d2, s);
-        const int oi = __shfl_sync(0xffffffffu, my_idx, s);
-        rank += kv_less(od, oi, my_d2, my_idx) ? 1 : 0;
-    }
-    const bool valid = lane < KC && my_idx != 0x7fffffff;
-    if (!valid) rank = 99;
-    const float my_d = valid ? sqrtf(my_d2) : INFINITY;
-    float dmin = my_d;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-
-    float my_w = 0.f, total = 1.f;
-    if (kSoft) {
-        const float e = valid ? expf(-a.alpha * (my_d - dmin)) : 0.f;
-        total = warp_sum(e);
-        if (l_tot != 0.f) total += l_tot * exp2f(-a2 * (r_star - dmin));
-        my_w = e / total;
-    }
-
-    if (valid && rank < a.topk) {
-        const size_t o = (size_t)g * a.topk + rank;
-        a.top_idx[o] = my_idx;
-        a.top_d[o] = my_d;
-        if (a.top_w) a.top_w[o] = my_w;
-        if (rank == 0) {
-            if (a.argmin) a.argmin[g] = my_idx;
-            if (a.row_min) a.row_min[g] = my_d;
-            if (a.row_sum) a.row_sum[g] = total;
-        }
-    }
+    float dk, dmin;
+    rescore_emit<kSoft>(a, g, b, lane, sel_idx, KC, l_tot, r_star, dk, dmin);
 
     // ---- certificate: every discarded column has candidate-pass key >= key16, i.e. a true distance of at least
     //      sqrt(key16 - E2) - (|x - x~| + |y - y~|) - rel * d16, E2 = accumulation error of the tensor-core key
-    {
-        const unsigned m = __ballot_sync(0xffffffffu, rank == a.topk - 1);
-        const float dk = m ? __shfl_sync(0xffffffffu, my_d, __ffs(m) - 1) : INFINITY;
-        if (lane == 0) {
-            float bound = 0.f, e2 = 0.f;
-            if (a.err_x) bound = a.err_x[g] + a.err_ymax[b];
-            if (a.tc_xx) e2 = 2e-6f * (a.tc_xx[g] + a.tc_yymax[b]);
-            bool ok;
-            if (key16 == INFINITY) ok = bound < INFINITY;            // every column is in the list (M < KC) unless the
-            else {                                                   // 16-bit conversion overflowed
-                const float d16 = sqrtf(fmaxf(key16 - e2, 0.f));
-                ok = dk < d16 - (bound + a.rel_bound * d16);
-            }
-            if (!ok) {
-                if (a.flag_list) a.flag_list[atomicAdd(a.flag_count, 1)] = g;
-                else if (a.tie_count) atomicAdd(a.tie_count, 1);
-            }
+    if (lane == 0) {
+        float bound = 0.f, e2 = 0.f;
+        if (a.err_x) bound = a.err_x[g] + a.err_ymax[b];
+        if (a.tc_xx) e2 = 2e-6f * (a.tc_xx[g] + a.tc_yymax[b]);
+        bool ok;
+        if (key16 == INFINITY) ok = bound < INFINITY;            // every column is in the list (M < KC) unless the
+        else {                                                   // 16-bit conversion overflowed
+            const float d16 = sqrtf(fmaxf(key16 - e2, 0.f));
+            ok = dk < d16 - (bound + a.rel_bound * d16);
+        }
+        if (!ok) {
+            if (a.flag_list) {
+                const int e = atomicAdd(a.flag_count, 1);
+                a.flag_list[e] = g;
+                // every column that can still belong to the top-k has an exact distance <= dk; the rescue scan
+                // evaluates d^2 in a different summation order (relative difference <= 1.6e-5), hence the slack
+                if (a.flag_thr) { a.flag_thr[e] = dk * dk * (1.f + 3e-5f); a.flag_r[e] = dmin; }
+            } else if (a.tie_count) atomicAdd(a.tie_count, 1);
         }
     }
+}
 
-    // ---- Pi . V  (10-sparse gather), lanes over the Dv output channels
-    if (kSoft && a.V && a.PiV) {
-        float wk[DVM_TOPK_MAX]; int jk[DVM_TOPK_MAX];
-#pragma unroll
-        for (int k = 0; k < DVM_TOPK_MAX; ++k) {
-            const unsigned m = __ballot_sync(0xffffffffu, rank == k);
-            const int src = m ? __ffs(m) - 1 : 0;
-            wk[k] = m ? __shfl_sync(0xffffffffu, my_w, src) : 0.f;
-            jk[k] = m ? __shfl_sync(0xffffffffu, my_idx, src) : 0;
-            if (k >= a.topk) wk[k] = 0.f;
+// =================================================================================================
+// 2b. rescue path for the (few) rows the 16-bit certificate rejects.  For such a row every column that can
+//     still belong to the top-k has an exact distance <= dk (the exact k-th best among the 16 candidates), so
+//     instead of a second top-k sweep the row needs a THRESHOLD SCAN: all columns with d^2 <= thr are listed
+//     (typically k .. k+2 of them), every other column only adds its exact softmax term to the row's mass.
+//     The scan is parallel over column chunks (grid = chunks x batch), deterministic (per-chunk partial
+//     masses summed in chunk order) and reads Y once per 8 flagged rows.
+// =================================================================================================
+constexpr int RESC_MAX = 4096;       // flagged rows handled by the rescue scan; more -> fp32 candidate pass
+constexpr int RESC_CAP = 32;         // listed columns per row; more (mass ties) -> fp32 pass for that row
+constexpr int RESC_NCH_MAX = 256;    // column chunks
+constexpr int RESC_ROWS = 8;         // flagged rows per group
+
+template <bool kSoft>
+__global__ void __launch_bounds__(256)
+rescue_scan_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M, int C,
+                   const int* __restrict__ flag_list, const int* __restrict__ flag_count,
+                   const float* __restrict__ flag_thr, const float* __restrict__ flag_r, float a2,
+                   int nch, int chunk, int* __restrict__ resc_cnt, int* __restrict__ resc_idx, float* __restrict__ resc_mass) {
+    __shared__ int s_slots[RESC_MAX];
+    __shared__ int s_n;
+    __shared__ __align__(16) float xs[RESC_ROWS][256];
+    __shared__ float s_thr[RESC_ROWS], s_ref[RESC_ROWS];
+    __shared__ float s_part[8][RESC_ROWS];
+    const int count = *flag_count;
+    if (count == 0 || count > RESC_MAX) return;
+    const int b = blockIdx.y, ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int c0 = ch * chunk, c1 = min(M, c0 + chunk);
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int e = tid; e < count; e += 256)
+        if (flag_list[e] / N == b) s_slots[atomicAdd(&s_n, 1)] = e;
+    __syncthreads();
+    const int n = s_n;
+    const float* Yb = Y + (size_t)b * M * C;
+    for (int g0 = 0; g0 < n; g0 += RESC_ROWS) {
+        __syncthreads();
+        for (int e = tid; e < RESC_ROWS * C; e += 256) {
+            const int r = e / C, c = e - r * C;
+            xs[r][c] = (g0 + r < n) ? __ldg(X + (size_t)flag_list[s_slots[g0 + r]] * C + c) : 0.f;
         }
-        const float* Vb = a.V + (size_t)b * a.M * a.Dv;
-        for (int dv = lane; dv < a.Dv; dv += 32) {
-            float acc = 0.f;
+        if (tid < RESC_ROWS) {
+            const bool ok = g0 + tid < n;
+            s_thr[tid] = ok ? flag_thr[s_slots[g0 + tid]] : -1.f;
+            s_ref[tid] = ok ? flag_r[s_slots[g0 + tid]] : 0.f;
+        }
+        __syncthreads();
+        float mass[RESC_ROWS];
 #pragma unroll
-            for (int k = 0; k < DVM_TOPK_MAX; ++k)
-                if (wk[k] != 0.f) acc = fmaf(wk[k], __ldg(Vb + (size_t)jk[k] * a.Dv + dv), acc);
-            a.PiV[(size_t)g * a.Dv + dv] = acc;
+        for (int r = 0; r < RESC_ROWS; ++r) mass[r] = 0.f;
+        for (int col = c0 + tid; col < c1; col += 256) {
+            float acc[RESC_ROWS];
+#pragma unroll
+            for (int r = 0; r < RESC_ROWS; ++r) acc[r] = 0.f;
+            const float* yp = Yb + (size_t)col * C;
+            for (int k = 0; k < C; k += 4) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(yp + k));
+#pragma unroll
+                for (int r = 0; r < RESC_ROWS; ++r) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[r][k]);      // warp-broadcast
+                    float d;
+                    d = xv.x - yv.x; acc[r] = fmaf(d, d, acc[r]);
+                    d = xv.y - yv.y; acc[r] = fmaf(d, d, acc[r]);
+                    d = xv.z - yv.z; acc[r] = fmaf(d, d, acc[r]);
+                    d = xv.w - yv.w; acc[r] = fmaf(d, d, acc[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RESC_ROWS; ++r) {
+                if (g0 + r < n) {
+                    if (acc[r] <= s_thr[r]) {
+                        const int slot = s_slots[g0 + r];
+                        const int q = atomicAdd(resc_cnt + slot, 1);
+                        if (q < RESC_CAP) resc_idx[(size_t)slot * RESC_CAP + q] = col;
+                    } else if (kSoft) {
+                        mass[r] += exp2f(-a2 * (sqrtf(acc[r]) - s_ref[r]));
+                    }
+                }
+            }
+        }
+        if (kSoft) {
+#pragma unroll
+            for (int r = 0; r < RESC_ROWS; ++r) {
+                const float v = warp_sum(mass[r]);
+                if (lane == 0) s_part[wid][r] = v;
+            }
+            __syncthreads();
+            if (tid < RESC_ROWS && g0 + tid < n) {
+                float t = 0.f;
+                for (int w = 0; w < 8; ++w) t += s_part[w][tid];
+                resc_mass[(size_t)s_slots[g0 + tid] * nch + ch] = t;
+            }
         }
     }
+}
+
+struct RescueArgs {
+    const int* flag_list; const int* flag_count; const float* flag_r;
+    const int* resc_cnt; const int* resc_idx; const float* resc_mass; int nch;
+    int* list2; int* count2;                       // rows that still need the fp32 candidate pass
+};
+
+template <bool kSoft>
+__global__ void __launch_bounds__(FIN_WARPS * 32) rescue_finalize_kernel(FinalizeArgs a, RescueArgs r) {
+    const int count = *r.flag_count;
+    if (count == 0) return;
+    if (count > RESC_MAX) {                        // too many: hand every flagged row to the fp32 pass
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) r.list2[e] = r.flag_list[e];
+        if (blockIdx.x == 0 && threadIdx.x == 0) *r.count2 = count;
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
+    if (w >= count) return;
+    const int g = r.flag_list[w];
+    const int n = r.resc_cnt[w];
+    if (n > RESC_CAP) {
+        if (lane == 0) r.list2[atomicAdd(r.count2, 1)] = g;
+        return;
+    }
+    const int sel_idx = lane < n ? r.resc_idx[(size_t)w * RESC_CAP + lane] : -1;
+    float l_other = 0.f;
+    if (kSoft) {
+        float t = 0.f;
+        for (int c = lane; c < r.nch; c += 32) t += r.resc_mass[(size_t)w * r.nch + c];
+        l_other = warp_sum(t);
+    }
+    float dk, dmin;
+    rescore_emit<kSoft>(a, g, g / a.N, lane, sel_idx, RESC_CAP, l_other, r.flag_r[w], dk, dmin);
 }
 
 static int launch_finalize(const FinalizeArgs& a, bool soft, int max_rows, cudaStream_t st) {
@@ -492,11 +650,14 @@ static void carve_cand(WsCarver& ws, size_t rows, int P, CandBuffers& cb) {
     cb.idx = ws.take<int>(rows * P * KC);
     cb.l = ws.take<float>(rows * P);
     cb.r = ws.take<float>(rows * P);
+    cb.t = ws.take<float>(rows * P);
 }
+
+struct RescueWs { float* flag_thr; float* flag_r; int* cnt; int* idx; float* mass; int* list2; };
 
 static size_t softmap_ws_layout(void* base, size_t cap, int B, int N, int M, int C, int prec,
                                 CandBuffers* simt, CandBuffers* tc, int** flag_list, int** stats_fallback,
-                                float** err_x, float** err_ymax, void** tc_ws, size_t* tc_ws_bytes) {
+                                float** err_x, float** err_ymax, void** tc_ws, size_t* tc_ws_bytes, RescueWs* resc = nullptr) {
     WsCarver ws(base, cap);
     const size_t rows = (size_t)B * N;
     CandBuffers c1{}, c2{};
@@ -510,6 +671,14 @@ static size_t softmap_ws_layout(void* base, size_t cap, int B, int N, int M, int
         ey = ws.take<float>(B);
         tb = tc_workspace_bytes(B, N, M, C);
         tws = ws.take<char>(tb);
+        RescueWs rw;
+        rw.flag_thr = ws.take<float>(rows);
+        rw.flag_r = ws.take<float>(rows);
+        rw.list2 = ws.take<int>(rows);
+        rw.cnt = ws.take<int>(RESC_MAX);
+        rw.idx = ws.take<int>((size_t)RESC_MAX * RESC_CAP);
+        rw.mass = ws.take<float>((size_t)RESC_MAX * RESC_NCH_MAX);
+        if (resc) *resc = rw;
     }
     if (simt) *simt = c1;
     if (tc) *tc = c2;
@@ -554,9 +723,9 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     if (C > 128) prec = DVM_PREC_FP32;
 
     CandBuffers simt{}, tc{};
-    int* flag_list; int* sfb; float* err_x; float* err_ymax; void* tws; size_t tws_bytes;
+    int* flag_list; int* sfb; float* err_x; float* err_ymax; void* tws; size_t tws_bytes; RescueWs rw{};
     const size_t need = softmap_ws_layout(ws, ws_bytes, B, N, M, C, prec, &simt, &tc, &flag_list, &sfb,
-                                          &err_x, &err_ymax, &tws, &tws_bytes);
+                                          &err_x, &err_ymax, &tws, &tws_bytes, &rw);
     if (!ws || need > ws_bytes) {
         set_error("dvm_softmap_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
         return DVM_ERR_WORKSPACE;
@@ -577,13 +746,36 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     }
     if ((rc = launch_cand_tc(X, Y, B, N, M, C, alpha, soft, prec, tc, err_x, err_ymax, &fa.tc_xx, &fa.tc_yymax, tws, tws_bytes, st))) return rc;
     fa.cb = tc; fa.rel_bound = 2e-5f; fa.err_x = err_x; fa.err_ymax = err_ymax;
-    fa.flag_list = flag_list; fa.flag_count = st_out;
+    fa.flag_list = flag_list; fa.flag_count = st_out; fa.flag_thr = rw.flag_thr; fa.flag_r = rw.flag_r;
+    DVM_CUDA(cudaMemsetAsync(rw.cnt, 0, RESC_MAX * sizeof(int), st));
     if ((rc = launch_finalize(fa, soft, rows, st))) return rc;
-    // fp32 recomputation of the uncertified rows (count lives on the device: no host sync): one CTA per row
-    // when there are few of them, the row-tile kernel otherwise (each kernel exits at once in the other case)
-    if ((rc = launch_rows_exact(X, Y, N, M, C, alpha, soft, flag_list, st_out, rows, simt, st))) return rc;
-    if ((rc = launch_cand_simt(X, Y, B, N, M, C, alpha, soft, flag_list, st_out, rows, simt, st))) return rc;
+    // rows the certificate rejected (count lives on the device: no host sync, every kernel below exits at once
+    // when it has nothing to do): threshold scan + exact emit; what even that cannot settle (> RESC_CAP columns
+    // inside the threshold, or > RESC_MAX flagged rows) goes to the fp32 candidate pass.
+    {
+        int nch = ceil_div(2 * kNumSM, B);
+        if (nch > RESC_NCH_MAX) nch = RESC_NCH_MAX;
+        if (nch > ceil_div(M, 64)) nch = ceil_div(M, 64);
+        const int chunk = ceil_div(M, nch);
+        nch = ceil_div(M, chunk);
+        const float a2 = alpha * kLog2e;
+        dim3 grid(nch, B);
+        if (soft) rescue_scan_kernel<true><<<grid, 256, 0, st>>>(X, Y, N, M, C, flag_list, st_out, rw.flag_thr, rw.flag_r, a2, nch, chunk, rw.cnt, rw.idx, rw.mass);
+        else      rescue_scan_kernel<false><<<grid, 256, 0, st>>>(X, Y, N, M, C, flag_list, st_out, rw.flag_thr, rw.flag_r, a2, nch, chunk, rw.cnt, rw.idx, rw.mass);
+        DVM_LAUNCH_CHECK();
+        RescueArgs ra{flag_list, st_out, rw.flag_r, rw.cnt, rw.idx, rw.mass, nch, rw.list2, st_out + 2};
+        FinalizeArgs fr = fa;
+        fr.flag_list = nullptr; fr.flag_count = nullptr; fr.flag_thr = nullptr; fr.flag_r = nullptr; fr.tie_count = nullptr;
+        const int fgrid = ceil_div(RESC_MAX, FIN_WARPS);
+        if (soft) rescue_finalize_kernel<true><<<fgrid, FIN_WARPS * 32, 0, st>>>(fr, ra);
+        else      rescue_finalize_kernel<false><<<fgrid, FIN_WARPS * 32, 0, st>>>(fr, ra);
+        DVM_LAUNCH_CHECK();
+    }
+    int* list2 = rw.list2; int* count2 = st_out + 2;
+    if ((rc = launch_rows_exact(X, Y, N, M, C, alpha, soft, list2, count2, rows, simt, st))) return rc;
+    if ((rc = launch_cand_simt(X, Y, B, N, M, C, alpha, soft, list2, count2, rows, simt, st))) return rc;
     fa.cb = simt; fa.rel_bound = 1e-5f; fa.err_x = nullptr; fa.err_ymax = nullptr; fa.tc_xx = nullptr; fa.tc_yymax = nullptr;
-    fa.row_list = flag_list; fa.row_count = st_out; fa.flag_list = nullptr; fa.flag_count = nullptr; fa.tie_count = st_out + 1;
+    fa.row_list = list2; fa.row_count = count2; fa.flag_list = nullptr; fa.flag_count = nullptr; fa.flag_thr = nullptr; fa.flag_r = nullptr;
+    fa.tie_count = st_out + 1;
     return launch_finalize(fa, soft, rows, st);
 }

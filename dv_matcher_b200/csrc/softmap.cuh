@@ -10,6 +10,7 @@ struct CandBuffers {
     int*   idx;     // [rows][P][KC]  column indices, -1 padded
     float* l;       // [rows][P]      sum over non-candidate columns of exp(-alpha (d - r))
     float* r;       // [rows][P]      reference distance of l (running min of the partial sweep)
+    float* t;       // [rows][P]      discard bound: every column the partial list dropped has d^2 >= t (INFINITY: none beyond key[KC-1])
     int    P;
 };
 

@@ -38,6 +38,8 @@ constexpr int TC_CHUNK = 16;               // columns per min-tree
 constexpr int TC_FLUSH_AT = 4;             // flush the pending buffers when any lane holds more than this
 constexpr int TC_CAP = TC_FLUSH_AT + TC_CHUNK;   // slots per lane: a chunk can append at most TC_CHUNK entries
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int TC_PRIME_STRIDE = 16;        // priming pass: every 16th tile
+constexpr int TC_PRIME_MIN_TILES = 128;     // ... when the sweep has at least this many tiles (M >= 16k)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers (forms cross-checked against CUTLASS's cute/arch/*sm100* and cutlass/arch/barrier.h)
@@ -98,6 +100,22 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory accesses by 32-bit shared-window address (one register instead of a generic pointer pair)
+__device__ __forceinline__ void sts_v2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ float2 lds_v2(uint32_t a) { float2 r; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float x) { asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float r; asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(r) : "r"(a) : "memory"); return r; }
 
 // K-major operand descriptors (version 1).  SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (SBO);
 // SWIZZLE_32B: rows of 32 B, 8-row atoms 256 B apart.  LBO is unused for swizzled K-major layouts (= 1).
@@ -186,77 +204,101 @@ tc_prep_kernel(const float* __restrict__ src, int rows_per_b, int rows_alloc, in
 struct TcParams {
     int N, M, KB;                // KB = Cpad / 64
     int tiles_total, tiles_per_split;
+    int tile_stride;             // 1 for the sweep; > 1: the priming pass visits every tile_stride-th tile only
+    int multi_split;             // column-split CTAs exchange thresholds through thr_global during the sweep
     float a2, cut_over_alpha;
     uint32_t idesc;
     const float* xx;             // [B*N]
-    unsigned* thr_global;        // [B*N] per-row threshold (true d^2 bits) shared by column-split CTAs (null when S == 1)
+    unsigned* thr_global;        // [B*N] per-row list threshold (true d^2 bits): written by the priming pass, refined
+                                 // with atomicMin by the sweep
     CandBuffers cb;
 };
 
 // Epilogue candidate handling (per thread = one row, 64 columns of every tile):
-//   * the KC best (key, idx) of the row live in REGISTERS as a sorted list;
+//   * the K best (key, idx) of the row live in REGISTERS as a sorted list;
 //   * per 16-column chunk a min-tree yields the chunk minimum; if it is below the row's "interesting" bound
 //     thr_hi = max(list threshold, softmax-window bound) the lane appends the interesting entries of the chunk
 //     to its pending buffer in shared memory (slot-major [slot][lane] -> conflict-free);
 //   * when any lane holds more than TC_FLUSH_AT entries the whole warp flushes: every lane inserts ITS OWN
 //     pending entries into its register list simultaneously (lane-parallel, ~10x cheaper than one divergent
 //     insertion per hit); evicted / rejected entries go to the row's softmax mass;
-//   * the threshold of a row is shared between its partial lists -- the two column halves of a CTA via
-//     shared memory, column-split CTAs via atomicMin in global memory.  Any value ever published is the
-//     KC-th best of KC real columns, hence >= the final merged KC-th best: stale reads are safe.
+//   * the list threshold of a row starts from the PRIMING pass (the 6th smallest key of a 1/32 column sample,
+//     i.e. roughly the 150th best of the row -- no "everything is a hit" start-up phase, ~4x fewer insertions)
+//     and is shared between the row's partial lists: the two column halves of a CTA via shared memory,
+//     column-split CTAs via atomicMin in global memory.  Whatever the threshold was, every column a partial
+//     list discarded has a key >= the list's final threshold, which is handed to finalize as the discard bound
+//     `t` -- so a threshold that turns out too tight costs a rescue scan, never a wrong answer.
 // Keys live in the half domain  key = (d~^2 - |x~|^2) / 2.
+constexpr int KP = 6;             // list length of the priming pass
+
+template <int K>
 struct EpiState {
-    TopList<KC> list;
-    float thr_list;        // append threshold: min(own KC-th best, thresholds published by the row's other lists)
+    TopList<K> list;
+    float thr_list;        // append threshold: min(own K-th best, primed / published thresholds of the row)
     float thr_mass;        // softmax window bound in the key domain (soft mode): entries in [thr_list, thr_mass) only add mass
-    float r, l;            // running min distance, mass of non-candidate columns relative to r
-    int cnt;               // pending entries in the lane's buffer
+    float thr_hi;          // max(thr_list, thr_mass): anything below is appended to the pending buffer
+    float kr, r;           // smallest key seen so far by this thread (over ALL its columns) and its distance
+    float l;               // mass of the non-candidate columns relative to r
+    uint32_t wr;           // write cursor into the lane's pending buffer (shared-window address, 256 B per slot)
 };
 
-template <bool kSoft>
-__device__ __forceinline__ void epi_mass_add(EpiState& st, float key, float xx, float a2) {
-    if (kSoft) {
-        // r is the smallest distance among EVERYTHING counted so far (list or mass): a list that adopted a
-        // tighter threshold from the row's other lists may hold only far entries, so a mass-only column can be
-        // closer than the list head -- rescale instead of evaluating exp2 of a large positive number.
-        const float d = sqrtf(fmaxf(fmaf(2.f, key, xx), 0.f));
-        if (d < st.r) { if (st.l != 0.f) st.l *= exp2f(-a2 * (st.r - d)); st.r = d; }
-        st.l += exp2f(-a2 * (d - st.r));
-    }
+__device__ __forceinline__ float ex2_approx(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
+__device__ __forceinline__ float key_to_dist(float key, float xx) { return sqrtf(fmaxf(fmaf(2.f, key, xx), 0.f)); }
+
+// softmax term of a non-candidate column this thread has already swept (key >= st.kr, exponent <= ~0).  These
+// terms are all below the 16 exact ones, so MUFU-approximate sqrt / exp2 (2 ulp each) is ample.
+__device__ __forceinline__ float epi_term(float key, float xx, float r, float a2) {
+    const float x = fmaxf(fmaf(2.f, key, xx), 1e-30f);
+    const float d = x * __frsqrt_rn(x);
+    return ex2_approx(-a2 * (d - r));
 }
 
-// lane-parallel flush of the pending buffers (warp-uniform trip count)
-template <bool kSoft>
-__device__ __forceinline__ void epi_flush(EpiState& st, const float2* buf, int lane, float xx, float a2, float coa) {
-    const int mx = __reduce_max_sync(kFull, st.cnt);
+// a chunk minimum below everything seen so far: move the reference point of the mass (rare: O(log M) times per
+// row).  r only has to be A reference distance used consistently for l, so the MUFU approximations are fine.
+template <int K>
+__device__ __forceinline__ void epi_new_min(EpiState<K>& st, float m, float xx, float a2, float coa) {
+    const float x = fmaxf(fmaf(2.f, m, xx), 1e-30f);
+    const float rn = x * __frsqrt_rn(x);
+    if (st.l != 0.f) st.l *= ex2_approx(-a2 * (st.r - rn));
+    st.kr = m; st.r = rn;
+    const float te = rn + coa;
+    st.thr_mass = 0.5f * (te * te - xx);
+    st.thr_hi = fmaxf(st.thr_list, st.thr_mass);
+}
+
+// lane-parallel flush of the pending buffers (warp-uniform trip count).  Per round every lane takes ITS next
+// pending entry: a list candidate is inserted (the sorted insertion only runs in rounds where some lane has
+// one), everything else -- and whatever an insertion evicts -- adds its softmax term.
+template <bool kSoft, int K>
+__device__ __forceinline__ void epi_flush(EpiState<K>& st, uint32_t buf_a, float xx, float a2) {
+    const int cnt = (int)((st.wr - buf_a) >> 8);
+    const int mx = __reduce_max_sync(kFull, cnt);
 #pragma unroll 1
     for (int e = 0; e < mx; ++e) {
-        if (e < st.cnt) {
-            const float2 kv = buf[e * 32 + lane];
-            const float key = kv.x;
-            if (key < st.list.worst()) {
-                const float ev = st.list.push(key, __float_as_int(kv.y));
-                if (kSoft) {
-                    const float rn = sqrtf(fmaxf(fmaf(2.f, st.list.key[0], xx), 0.f));
-                    if (rn < st.r) { if (st.l != 0.f) st.l *= exp2f(-a2 * (st.r - rn)); st.r = rn; }
-                    if (ev != INFINITY) epi_mass_add<kSoft>(st, ev, xx, a2);
-                }
-            } else {
-                epi_mass_add<kSoft>(st, key, xx, a2);       // beaten since it was appended: mass only
-            }
+        const bool active = e < cnt;
+        float2 kv = make_float2(INFINITY, 0.f);
+        if (active) kv = lds_v2(buf_a + e * 256);
+        const bool cand = kv.x < st.list.worst();
+        float out = kv.x;
+        if (__any_sync(kFull, cand)) {
+            if (cand) out = st.list.push(kv.x, __float_as_int(kv.y));
         }
+        if (kSoft && out != INFINITY) st.l += epi_term(out, xx, st.r, a2);
     }
-    st.cnt = 0;
+    st.wr = buf_a;
     st.thr_list = fminf(st.thr_list, st.list.worst());
-    if (kSoft && st.r != INFINITY) { const float te = st.r + coa; st.thr_mass = 0.5f * (te * te - xx); }
+    st.thr_hi = kSoft ? fmaxf(st.thr_list, st.thr_mass) : st.thr_list;
 }
 
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float min4(float a, float b, float c, float d) { return fminf(fminf(a, b), fminf(c, d)); }
 
-template <bool kSoft>
+// kPrime: priming pass -- strided tile sample, K = KP, hard mode, only output is thr_global.
+template <bool kSoft, bool kPrime>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXe,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYe, const TcParams p) {
+    constexpr int K = kPrime ? KP : KC;
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzled operand tiles need 1024-byte alignment (checked below)
     const int unit = p.KB * TC_BLK_BYTES + TC_EXT_BYTES;  // one 128-row operand block, all of K
     uint8_t* Xs = smem;                                   // [2 sub-blocks][KB x 16 KB | 4 KB]
@@ -271,12 +313,14 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     uint64_t* xfull = tempty + 2;          // [1]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfull + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction: lives in uniform registers
+    const int lane = threadIdx.x & 31;
     const int b = blockIdx.z;
     const int split = blockIdx.y;
     const int row0 = blockIdx.x * TC_BM;
     const int tile0 = split * p.tiles_per_split;
-    const int ntiles = min(p.tiles_per_split, p.tiles_total - tile0);
+    const int span = min(p.tiles_per_split, p.tiles_total - tile0);
+    const int ntiles = (span + p.tile_stride - 1) / p.tile_stride;     // tiles tile0 + it * tile_stride
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -311,7 +355,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 mbar_wait(empty + s, ph ^ 1);
                 mbar_arrive_expect_tx(full + s, unit);
                 uint8_t* dst = Ys + s * unit;
-                const int col0 = (tile0 + it) * TC_BN;
+                const int col0 = (tile0 + it * p.tile_stride) * TC_BN;
                 for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(&tmY, full + s, dst + kb * TC_BLK_BYTES, kb * TC_KBLK, col0, b);
                 tma_load_3d(&tmYe, full + s, dst + p.KB * TC_BLK_BYTES, 0, col0, b);
             }
@@ -356,93 +400,95 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int row = row0 + rloc;
         const bool row_ok = row < p.N;
         const float xx = row_ok ? __ldg(p.xx + (size_t)b * p.N + row) : 0.f;
-        float2* buf = cand_buf + ew * TC_CAP * 32;
-        volatile float* thr_mine = thr_sh + half * TC_BM + rloc;
-        volatile float* thr_other = thr_sh + (1 - half) * TC_BM + rloc;
-        unsigned* thr_g = p.thr_global ? p.thr_global + (size_t)b * p.N + row : nullptr;    // true-domain d^2 bits
-        *thr_mine = INFINITY;
-        EpiState st;
+        const uint32_t buf_a = smem_u32(cand_buf) + (uint32_t)(ew * TC_CAP * 32 + lane) * 8u;
+        const uint32_t thr_mine_a = smem_u32(thr_sh) + (uint32_t)(half * TC_BM + rloc) * 4u;
+        const uint32_t thr_other_a = smem_u32(thr_sh) + (uint32_t)((1 - half) * TC_BM + rloc) * 4u;
+        unsigned* thr_g = p.thr_global + (size_t)b * p.N + (row_ok ? row : 0);     // true-domain d^2 bits
+        sts_f32(thr_mine_a, INFINITY);
+        EpiState<K> st;
         st.list.init();
-        st.thr_list = row_ok ? INFINITY : -INFINITY;       // padding rows never hit
-        st.thr_mass = -INFINITY;                           // no mass-only entries until the running minimum exists
-        st.r = INFINITY; st.l = 0.f; st.cnt = 0;
+        st.thr_list = -INFINITY;                           // padding rows never hit
+        if (row_ok) st.thr_list = kPrime ? INFINITY : 0.5f * (__uint_as_float(__ldcg(thr_g)) - xx);
+        st.thr_mass = -INFINITY;                           // no window terms until the running minimum exists
+        st.thr_hi = st.thr_list;
+        st.kr = INFINITY; st.r = INFINITY; st.l = 0.f; st.wr = buf_a;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * TC_BN + half * 64;
+#pragma unroll 1
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int col0 = (tile0 + it) * TC_BN + half * 64;
-            // pick up thresholds published by the row's other lists -- only once the own list is full, so that
-            // the own running minimum (the reference point of the softmax mass) exists before anything is rejected
-            if (row_ok && st.list.worst() != INFINITY) {
-                float t = *thr_other;
-                if (thr_g) t = fminf(t, 0.5f * (__uint_as_float(__ldcg(thr_g)) - xx));
-                st.thr_list = fminf(st.thr_list, t);
+            const int col0 = (tile0 + it * p.tile_stride) * TC_BN + half * 64;
+            if (!kPrime && row_ok) {                        // thresholds published by the row's other lists
+                float t = lds_f32(thr_other_a);
+                if (p.multi_split) t = fminf(t, 0.5f * (__uint_as_float(__ldcg(thr_g)) - xx));
+                if (t < st.thr_list) { st.thr_list = t; st.thr_hi = kSoft ? fmaxf(t, st.thr_mass) : t; }
             }
             mbar_wait(tfull + acc, aph);
             tc_fence_after();
 #pragma unroll 1
-            for (int c2 = 0; c2 < 2; ++c2) {
-                float v[32];
-                tc_ld32(t_lane + acc * 2 * TC_BN + c2 * 32, v);
-                if (c2 == 1) {                              // all of this tile is in registers: hand the stage back
+            for (int c = 0; c < 64 / TC_CHUNK; ++c) {
+                float k[TC_CHUNK];
+                tc_ld16(t_lane + acc * 2 * TC_BN + c * TC_CHUNK, k);
+                if (c == 64 / TC_CHUNK - 1) {               // all of this tile is in registers: hand the stage back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty + acc);
                 }
+                // chunk minimum: 8 three-input min instructions
+                const float m = fminf(min3(min3(k[0], k[1], k[2]), min3(k[3], k[4], k[5]), min3(k[6], k[7], k[8])),
+                                      min3(min3(k[9], k[10], k[11]), min3(k[12], k[13], k[14]), k[15]));
+                const bool slow = m < st.thr_hi;
+                if (__any_sync(kFull, slow)) {
+                    if (slow) {
+                        const int cbase = col0 + c * TC_CHUNK;
+                        if (kSoft && m < st.kr) epi_new_min(st, m, xx, p.a2, p.cut_over_alpha);
+                        const float th = st.thr_hi;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float* k = v + c * TC_CHUNK;
-                    const float g0 = min4(k[0], k[1], k[2], k[3]);
-                    const float g1 = min4(k[4], k[5], k[6], k[7]);
-                    const float g2 = min4(k[8], k[9], k[10], k[11]);
-                    const float g3 = min4(k[12], k[13], k[14], k[15]);
-                    const float m = min4(g0, g1, g2, g3);
-                    const float thr_hi = kSoft ? fmaxf(st.thr_list, st.thr_mass) : st.thr_list;
-                    const bool slow = m < thr_hi;
-                    if (__any_sync(kFull, slow)) {
-                        if (slow) {
-                            const int cbase = col0 + c2 * 32 + c * TC_CHUNK;
-                            const float gq[4] = {g0, g1, g2, g3};
+                        for (int q = 0; q < 4; ++q) {
+                            if (min4(k[q * 4], k[q * 4 + 1], k[q * 4 + 2], k[q * 4 + 3]) < th) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (gq[q] < thr_hi) {
-#pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        const float kk = k[q * 4 + t];
-                                        if (kk < thr_hi) {
-                                            buf[st.cnt * 32 + lane] = make_float2(kk, __int_as_float(cbase + q * 4 + t));
-                                            ++st.cnt;
-                                        }
+                                for (int t = 0; t < 4; ++t) {
+                                    if (k[q * 4 + t] < th) {       // list candidate or softmax-window term: sorted out by the flush
+                                        sts_v2(st.wr, k[q * 4 + t], __int_as_float(cbase + q * 4 + t));
+                                        st.wr += 256;
                                     }
                                 }
                             }
                         }
-                        if (__any_sync(kFull, st.cnt > TC_FLUSH_AT)) {
-                            epi_flush<kSoft>(st, buf, lane, xx, p.a2, p.cut_over_alpha);
-                            if (row_ok) {
-                                const float w = st.list.worst();
-                                *thr_mine = w;
-                                if (w != INFINITY) st.thr_list = fminf(st.thr_list, *thr_other);
-                                if (thr_g && w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
-                            }
+                    }
+                    if (__any_sync(kFull, st.wr > buf_a + TC_FLUSH_AT * 256)) {
+                        epi_flush<kSoft>(st, buf_a, xx, p.a2);
+                        if (!kPrime && row_ok) {
+                            const float w = st.list.worst();
+                            sts_f32(thr_mine_a, w);
+                            const float t = lds_f32(thr_other_a);
+                            if (t < st.thr_list) { st.thr_list = t; st.thr_hi = kSoft ? fmaxf(t, st.thr_mass) : t; }
+                            if (p.multi_split && w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
                         }
                     }
                 }
             }
         }
-        epi_flush<kSoft>(st, buf, lane, xx, p.a2, p.cut_over_alpha);
+        epi_flush<kSoft>(st, buf_a, xx, p.a2);
         if (row_ok) {
-            const size_t g_row = (size_t)b * p.N + row;
-            const int pidx = split * 2 + half;
-            const size_t base = (g_row * p.cb.P + pidx) * KC;
+            if (kPrime) {
+                const float w = st.list.worst();
+                if (w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
+            } else {
+                const size_t g_row = (size_t)b * p.N + row;
+                const int pidx = split * 2 + half;
+                const size_t base = (g_row * p.cb.P + pidx) * KC;
 #pragma unroll
-            for (int t = 0; t < KC; ++t) {
-                const float k = st.list.key[t];
-                p.cb.key[base + t] = k == INFINITY ? INFINITY : fmaxf(fmaf(2.f, k, xx), 0.f);    // back to the true d^2 domain
-                p.cb.idx[base + t] = st.list.idx[t];
+                for (int t = 0; t < K; ++t) {
+                    const float k = st.list.key[t];
+                    p.cb.key[base + t] = k == INFINITY ? INFINITY : fmaxf(fmaf(2.f, k, xx), 0.f);    // back to the true d^2 domain
+                    p.cb.idx[base + t] = st.list.idx[t];
+                }
+                p.cb.l[g_row * p.cb.P + pidx] = st.l;
+                p.cb.r[g_row * p.cb.P + pidx] = st.r;
+                // discard bound of this partial list (true domain): everything it dropped has a key >= thr_list
+                p.cb.t[g_row * p.cb.P + pidx] = st.thr_list == INFINITY ? INFINITY : fmaxf(fmaf(2.f, st.thr_list, xx), 0.f);
             }
-            p.cb.l[g_row * p.cb.P + pidx] = st.l;
-            p.cb.r[g_row * p.cb.P + pidx] = st.r;
         }
     }
 
@@ -584,24 +630,33 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     const uint32_t fmt = bf16 ? 1u : 0u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_SUB >> 4) << 24);
     p.xx = w.xx; p.cb = cb;
-    p.thr_global = nullptr;
-    if (S > 1) {                                     // +inf bit pattern: 0x7f800000 (byte-wise memset cannot write it)
-        p.thr_global = w.thr_g;
-        fill_u32_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(w.thr_g, 0x7f800000u, B * N);
-        DVM_LAUNCH_CHECK();
-    }
+    p.thr_global = w.thr_g;
+    p.multi_split = S > 1;
+    p.tile_stride = 1;
+    fill_u32_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(w.thr_g, 0x7f800000u, B * N);    // +inf (memset cannot write it)
+    DVM_LAUNCH_CHECK();
 
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
     const size_t smem = (2 + TC_NST) * unit + (size_t)TC_EPI_WARPS * TC_CAP * 32 * 8 + 2 * TC_BM * sizeof(float) + 128;
-    auto kern = soft ? softmap_cand_tc_kernel<true> : softmap_cand_tc_kernel<false>;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[soft]) {
-        DVM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done[soft] = true;
+    auto kern = soft ? softmap_cand_tc_kernel<true, false> : softmap_cand_tc_kernel<false, false>;
+    auto kprime = softmap_cand_tc_kernel<false, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DVM_CUDA(cudaFuncSetAttribute(kprime, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
     }
     if (smem > 227 * 1024) { set_error("launch_cand_tc: C=%d needs %zu bytes of shared memory", C, smem); return DVM_ERR_UNSUPPORTED; }
-    dim3 grid(ceil_div(N, TC_BM), S, B);
     prof_begin(st);
+    if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 16th tile (6 % of the sweep's MMA work)
+        TcParams pp = p;
+        pp.tile_stride = TC_PRIME_STRIDE; pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
+        dim3 gridp(ceil_div(N, TC_BM), 1, B);
+        kprime<<<gridp, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, pp);
+        DVM_LAUNCH_CHECK();
+    }
+    dim3 grid(ceil_div(N, TC_BM), S, B);
     kern<<<grid, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, p);
     prof_end(st);
     DVM_LAUNCH_CHECK();
