@@ -4,8 +4,9 @@
 
 namespace dvm {
 
-int launch_knn3(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
-                int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, cudaStream_t st);
+int launch_knn3_auto(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
+                     int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t knn3_grid_workspace_bytes(int B, int M);
 
 // ------------------------------------------------------------------------------------------------
 // FPS: one CTA per cloud, K dependent iterations.  Each iteration: masked min-update of the running
@@ -172,6 +173,7 @@ extern "C" size_t dvm_graph_workspace_bytes(int B, int N, int K) {
     ws.take<float>((size_t)B * K * 3);      // node coordinates
     ws.take<float>((size_t)B * N * 3);      // squared distances vertex -> 3 nodes
     ws.take<double>((size_t)B * N * 2);     // fp64 squared NN distances
+    ws.take<char>(knn3_grid_workspace_bytes(B, N));   // grid scratch of the three k-NN queries (largest: N points)
     return align_up(ws.off, 256);
 }
 
@@ -189,15 +191,17 @@ extern "C" int dvm_graph_weights(const float* xyz, const int64_t* nodes_idx, int
     float* nodes_xyz = ws.take<float>((size_t)B * K * 3);
     float* d2 = ws.take<float>((size_t)B * N * 3);
     double* d2nn = ws.take<double>((size_t)B * N * 2);
+    const size_t gbytes = knn3_grid_workspace_bytes(B, N);
+    void* gws = ws.take<char>(gbytes);
     gather_nodes_kernel<<<dim3(ceil_div(K, 256), B), 256, 0, st>>>(xyz, nodes_idx, N, K, nodes_xyz);
     DVM_LAUNCH_CHECK();
     int rc;
     // 3 nearest nodes per vertex, exact fp32 form (topk(3) of -geod[nodes].T, :186-188)
-    if ((rc = launch_knn3(xyz, nodes_xyz, B, N, K, 3, false, influence, nullptr, d2, nullptr, st))) return rc;
+    if ((rc = launch_knn3_auto(xyz, nodes_xyz, B, N, K, 3, false, influence, nullptr, d2, nullptr, gws, gbytes, st))) return rc;
     // node ring: KDTree(nodes).query(nodes, 9), fp64 (:181-183)
-    if ((rc = launch_knn3(nodes_xyz, nodes_xyz, B, K, K, 9, true, ring, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_knn3_auto(nodes_xyz, nodes_xyz, B, K, K, 9, true, ring, nullptr, nullptr, nullptr, gws, gbytes, st))) return rc;
     // sigma = 20 * mean NN spacing: KDTree(vertices).query(vertices, 2)[:,1], fp64 (:190-192)
-    if ((rc = launch_knn3(xyz, xyz, B, N, N, 2, true, nullptr, nullptr, nullptr, d2nn, st))) return rc;
+    if ((rc = launch_knn3_auto(xyz, xyz, B, N, N, 2, true, nullptr, nullptr, nullptr, d2nn, gws, gbytes, st))) return rc;
     sigma_kernel<<<B, 1024, 0, st>>>(d2nn, N, sigma);
     DVM_LAUNCH_CHECK();
     weights_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(d2, sigma, N, dists, weights);

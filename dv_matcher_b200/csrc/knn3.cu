@@ -120,6 +120,17 @@ static int launch_knn3_k(const float* Q, const float* R, int B, int N, int M, in
     return 0;
 }
 
+size_t knn3_grid_workspace_bytes(int B, int M);
+int launch_knn3_grid(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
+                     int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* ws, size_t ws_bytes, cudaStream_t st);
+
+constexpr int KNN_GRID_MIN_M = 1024;      // below this the brute-force sweep is as fast and one launch
+
+// grid search when the caller provided scratch and the reference cloud is big enough, brute force otherwise;
+// both give bit-identical results
+int launch_knn3_auto(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
+                     int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* ws, size_t ws_bytes, cudaStream_t st);
+
 int launch_knn3(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
                 int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, cudaStream_t st) {
 #define DVM_KNN_DISPATCH(T)                                                                       \
@@ -129,6 +140,13 @@ int launch_knn3(const float* Q, const float* R, int B, int N, int M, int k, bool
     else              return launch_knn3_k<T, 16>(Q, R, B, N, M, k, idx64, idx32, d2f, d2d, st);
     if (f64) { DVM_KNN_DISPATCH(double) } else { DVM_KNN_DISPATCH(float) }
 #undef DVM_KNN_DISPATCH
+}
+
+int launch_knn3_auto(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
+                     int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws && M >= KNN_GRID_MIN_M && ws_bytes >= knn3_grid_workspace_bytes(B, M))
+        return launch_knn3_grid(Q, R, B, N, M, k, f64, idx64, idx32, d2f, d2d, ws, ws_bytes, st);
+    return launch_knn3(Q, R, B, N, M, k, f64, idx64, idx32, d2f, d2d, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -168,22 +186,33 @@ __global__ void chamfer_bwd_kernel(const float* __restrict__ a, const float* __r
 
 using namespace dvm;
 
+extern "C" size_t dvm_knn3_workspace_bytes(int B, int N, int M) {
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    return M >= KNN_GRID_MIN_M ? knn3_grid_workspace_bytes(B, M) : 0;
+}
+
+extern "C" size_t dvm_chamfer_workspace_bytes(int B, int N, int M) {
+    if (B <= 0 || N <= 0 || M <= 0) return 0;
+    const size_t a = dvm_knn3_workspace_bytes(B, N, M), b = dvm_knn3_workspace_bytes(B, M, N);
+    return a > b ? a : b;
+}
+
 extern "C" int dvm_knn3(const float* Q, const float* R, int B, int N, int M, int k, int use_f64,
-                        int64_t* idx, int32_t* idx32, float* d2, double* d2_f64, void* stream) {
+                        int64_t* idx, int32_t* idx32, float* d2, double* d2_f64, void* ws, size_t ws_bytes, void* stream) {
     DVM_CHECK_ARG(Q && R, "dvm_knn3: null input");
     DVM_CHECK_ARG(B > 0 && N > 0 && M > 0, "dvm_knn3: empty problem (B=%d N=%d M=%d)", B, N, M);
     DVM_CHECK_ARG(k >= 1 && k <= DVM_KNN_MAX && k <= M, "dvm_knn3: k=%d must be in [1, min(16, M=%d)]", k, M);
     DVM_CHECK_ARG(B <= 65535, "dvm_knn3: B=%d too large", B);
-    return launch_knn3(Q, R, B, N, M, k, use_f64 != 0, idx, idx32, d2, d2_f64, (cudaStream_t)stream);
+    return launch_knn3_auto(Q, R, B, N, M, k, use_f64 != 0, idx, idx32, d2, d2_f64, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int dvm_chamfer_fwd(const float* a, const float* b, int B, int N, int M,
-                               float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* stream) {
+                               float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes, void* stream) {
     DVM_CHECK_ARG(a && b && dist1 && dist2 && idx1 && idx2, "dvm_chamfer_fwd: null pointer");
     DVM_CHECK_ARG(B > 0 && N > 0 && M > 0 && B <= 65535, "dvm_chamfer_fwd: bad sizes (B=%d N=%d M=%d)", B, N, M);
-    int rc = launch_knn3(a, b, B, N, M, 1, false, nullptr, idx1, dist1, nullptr, (cudaStream_t)stream);
+    int rc = launch_knn3_auto(a, b, B, N, M, 1, false, nullptr, idx1, dist1, nullptr, ws, ws_bytes, (cudaStream_t)stream);
     if (rc) return rc;
-    return launch_knn3(b, a, B, M, N, 1, false, nullptr, idx2, dist2, nullptr, (cudaStream_t)stream);
+    return launch_knn3_auto(b, a, B, M, N, 1, false, nullptr, idx2, dist2, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int dvm_chamfer_bwd(const float* a, const float* b, const int32_t* idx1, const int32_t* idx2,

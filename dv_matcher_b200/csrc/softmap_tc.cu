@@ -66,6 +66,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
+// wait used by the 16 epilogue warps: back off between probes so that warps that are ahead do not take issue
+// slots from the warp the CTA is waiting for
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    while (!done) {
+        __nanosleep(40);
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -101,7 +117,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+// asynchronous TMEM load of 16 columns (one row per thread) ...
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, float (&v)[16]) {
     uint32_t* u = reinterpret_cast<uint32_t*>(v);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -109,7 +126,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
         : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
           "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// ... and the wait that makes its registers valid: they are in/out operands so that no use can be scheduled
+// between the load and the wait
+__device__ __forceinline__ void tc_ld16_wait(float (&v)[16]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+          "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+        :: "memory");
 }
 // shared-memory accesses by 32-bit shared-window address (one register instead of a generic pointer pair)
 __device__ __forceinline__ void sts_v2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
@@ -293,6 +318,45 @@ __device__ __forceinline__ void epi_flush(EpiState<K>& st, uint32_t buf_a, float
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float min4(float a, float b, float c, float d) { return fminf(fminf(a, b), fminf(c, d)); }
 
+// one 16-column chunk of one row: min-tree, slow path (append interesting entries), flush when a buffer fills up
+template <bool kSoft, bool kPrime, int K>
+__device__ __forceinline__ void process_chunk(EpiState<K>& st, const float (&k)[TC_CHUNK], int cbase, uint32_t buf_a,
+                                              uint32_t thr_mine_a, uint32_t thr_other_a, unsigned* thr_g, bool row_ok,
+                                              float xx, const TcParams& p) {
+    // chunk minimum: 8 three-input min instructions
+    const float m = fminf(min3(min3(k[0], k[1], k[2]), min3(k[3], k[4], k[5]), min3(k[6], k[7], k[8])),
+                          min3(min3(k[9], k[10], k[11]), min3(k[12], k[13], k[14]), k[15]));
+    const bool slow = m < st.thr_hi;
+    if (__any_sync(kFull, slow)) {
+        if (slow) {
+            if (kSoft && m < st.kr) epi_new_min(st, m, xx, p.a2, p.cut_over_alpha);
+            const float th = st.thr_hi;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (min4(k[q * 4], k[q * 4 + 1], k[q * 4 + 2], k[q * 4 + 3]) < th) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (k[q * 4 + t] < th) {       // list candidate or softmax-window term: sorted out by the flush
+                            sts_v2(st.wr, k[q * 4 + t], __int_as_float(cbase + q * 4 + t));
+                            st.wr += 256;
+                        }
+                    }
+                }
+            }
+        }
+        if (__any_sync(kFull, st.wr > buf_a + TC_FLUSH_AT * 256)) {
+            epi_flush<kSoft>(st, buf_a, xx, p.a2);
+            if (!kPrime && row_ok) {
+                const float w = st.list.worst();
+                sts_f32(thr_mine_a, w);
+                const float t = lds_f32(thr_other_a);
+                if (t < st.thr_list) { st.thr_list = t; st.thr_hi = kSoft ? fmaxf(t, st.thr_mass) : t; }
+                if (p.multi_split && w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
+            }
+        }
+    }
+}
+
 // kPrime: priming pass -- strided tile sample, K = KP, hard mode, only output is thr_global.
 template <bool kSoft, bool kPrime>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -418,56 +482,34 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int col0 = (tile0 + it * p.tile_stride) * TC_BN + half * 64;
-            if (!kPrime && row_ok) {                        // thresholds published by the row's other lists
-                float t = lds_f32(thr_other_a);
-                if (p.multi_split) t = fminf(t, 0.5f * (__uint_as_float(__ldcg(thr_g)) - xx));
+            // thresholds published by the row's other lists: the global one (other column splits) is fetched before
+            // the wait for the accumulator and consumed after it, so its latency hides behind the MMA
+            unsigned tg_bits = 0x7f800000u;
+            if (!kPrime && p.multi_split && row_ok && (it & 3) == 0) tg_bits = __ldcg(thr_g);
+            mbar_wait_backoff(tfull + acc, aph);
+            tc_fence_after();
+            if (!kPrime && row_ok) {
+                const float t = fminf(lds_f32(thr_other_a), 0.5f * (__uint_as_float(tg_bits) - xx));
                 if (t < st.thr_list) { st.thr_list = t; st.thr_hi = kSoft ? fmaxf(t, st.thr_mass) : t; }
             }
-            mbar_wait(tfull + acc, aph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 64 / TC_CHUNK; ++c) {
-                float k[TC_CHUNK];
-                tc_ld16(t_lane + acc * 2 * TC_BN + c * TC_CHUNK, k);
-                if (c == 64 / TC_CHUNK - 1) {               // all of this tile is in registers: hand the stage back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty + acc);
-                }
-                // chunk minimum: 8 three-input min instructions
-                const float m = fminf(min3(min3(k[0], k[1], k[2]), min3(k[3], k[4], k[5]), min3(k[6], k[7], k[8])),
-                                      min3(min3(k[9], k[10], k[11]), min3(k[12], k[13], k[14]), k[15]));
-                const bool slow = m < st.thr_hi;
-                if (__any_sync(kFull, slow)) {
-                    if (slow) {
-                        const int cbase = col0 + c * TC_CHUNK;
-                        if (kSoft && m < st.kr) epi_new_min(st, m, xx, p.a2, p.cut_over_alpha);
-                        const float th = st.thr_hi;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (min4(k[q * 4], k[q * 4 + 1], k[q * 4 + 2], k[q * 4 + 3]) < th) {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    if (k[q * 4 + t] < th) {       // list candidate or softmax-window term: sorted out by the flush
-                                        sts_v2(st.wr, k[q * 4 + t], __int_as_float(cbase + q * 4 + t));
-                                        st.wr += 256;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (__any_sync(kFull, st.wr > buf_a + TC_FLUSH_AT * 256)) {
-                        epi_flush<kSoft>(st, buf_a, xx, p.a2);
-                        if (!kPrime && row_ok) {
-                            const float w = st.list.worst();
-                            sts_f32(thr_mine_a, w);
-                            const float t = lds_f32(thr_other_a);
-                            if (t < st.thr_list) { st.thr_list = t; st.thr_hi = kSoft ? fmaxf(t, st.thr_mass) : t; }
-                            if (p.multi_split && w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
-                        }
-                    }
-                }
-            }
+            const uint32_t taddr = t_lane + acc * 2 * TC_BN;
+            // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
+            float ka[TC_CHUNK], kb[TC_CHUNK];
+            tc_ld16_issue(taddr, ka);
+            tc_ld16_wait(ka);
+            tc_ld16_issue(taddr + TC_CHUNK, kb);
+            process_chunk<kSoft, kPrime>(st, ka, col0, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
+            tc_ld16_wait(kb);
+            tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
+            process_chunk<kSoft, kPrime>(st, kb, col0 + TC_CHUNK, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
+            tc_ld16_wait(ka);
+            tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
+            process_chunk<kSoft, kPrime>(st, ka, col0 + 2 * TC_CHUNK, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
+            tc_ld16_wait(kb);
+            tc_fence_before();                               // all of this tile is in registers: hand the stage back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+            process_chunk<kSoft, kPrime>(st, kb, col0 + 3 * TC_CHUNK, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
         }
         epi_flush<kSoft>(st, buf_a, xx, p.a2);
         if (row_ok) {

@@ -95,8 +95,9 @@ def sparse_transfer_bwd(idx, w, y, d_out, need_dw=True, need_dy=True):
     return dw, dy
 
 
-def knn3(q, r, k, f64=False, want_d2=False, idx_dtype=torch.int64):
-    """Exact brute-force k-NN on 3-D points: idx [B,N,k] (+ squared distances)."""
+def knn3(q, r, k, f64=False, want_d2=False, idx_dtype=torch.int64, algo="auto"):
+    """Exact k-NN on 3-D points: idx [B,N,k] (+ squared distances).  algo: "auto" (uniform grid for reference
+    clouds >= 1024 points, else brute force) or "brute"; both give bit-identical results."""
     lib = _lib.load()
     q, r = f32c(q), f32c(r)
     require_device(q)
@@ -108,12 +109,17 @@ def knn3(q, r, k, f64=False, want_d2=False, idx_dtype=torch.int64):
     d2 = torch.empty(B, N, k, dtype=torch.float64 if f64 else torch.float32, device=q.device) if want_d2 else None
     i64 = ptr(idx) if idx_dtype == torch.int64 else None
     i32 = ptr(idx) if idx_dtype == torch.int32 else None
+    ws = None
+    if algo != "brute":
+        nbytes = lib.dvm_knn3_workspace_bytes(B, N, M)
+        ws = _lib.workspace.get(nbytes, q.device, "knn3") if nbytes else None
     check(lib.dvm_knn3(ptr(q), ptr(r), B, N, M, int(k), int(bool(f64)), i64, i32,
-                       ptr(d2) if (want_d2 and not f64) else None, ptr(d2) if (want_d2 and f64) else None, stream_ptr()), "dvm_knn3")
+                       ptr(d2) if (want_d2 and not f64) else None, ptr(d2) if (want_d2 and f64) else None,
+                       ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()), "dvm_knn3")
     return (idx, d2) if want_d2 else idx
 
 
-def chamfer_fwd(a, b):
+def chamfer_fwd(a, b, algo="auto"):
     lib = _lib.load()
     a, b = f32c(a), f32c(b)
     require_device(a)
@@ -124,7 +130,12 @@ def chamfer_fwd(a, b):
     d2 = torch.empty(B, M, dtype=torch.float32, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
     i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
-    check(lib.dvm_chamfer_fwd(ptr(a), ptr(b), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2), stream_ptr()), "dvm_chamfer_fwd")
+    ws = None
+    if algo != "brute":
+        nbytes = lib.dvm_chamfer_workspace_bytes(B, N, M)
+        ws = _lib.workspace.get(nbytes, dev, "knn3") if nbytes else None
+    check(lib.dvm_chamfer_fwd(ptr(a), ptr(b), B, N, M, ptr(d1), ptr(d2), ptr(i1), ptr(i2),
+                              ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()), "dvm_chamfer_fwd")
     return d1, d2, i1, i2
 
 

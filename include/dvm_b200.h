@@ -65,8 +65,9 @@ int         dvm_profile_read(double* total_ms, int* brackets);
  *   top_w   f32[B,N,topk]   top_d   f32[B,N,topk] (exact fp32 Euclidean distances)
  *   row_min f32[B,N] (= d of the nearest column)   row_sum f32[B,N] (= sum_j exp(-alpha (d_j - row_min)))
  *   PiV     f32[B,N,Dv]
- *   stats   int32[4]: [0] rows whose top-k the low-precision candidate pass could not certify and
- *                     that were recomputed by the fp32 pass, [1..3] reserved
+ *   stats   int32[4]: [0] rows whose top-k the 16-bit candidate pass could not certify (settled exactly by the
+ *                     rescue scan), [1] exact fp32 near-ties at rank topk / topk+1, [2] rows that needed the full
+ *                     fp32 candidate pass, [3] reserved
  * ------------------------------------------------------------------------------------------ */
 size_t dvm_softmap_workspace_bytes(int B, int N, int M, int C, int prec);
 int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
@@ -99,14 +100,18 @@ int dvm_sparse_transfer_bwd(const int32_t* idx, const float* w, const float* Y, 
  * KD-tree queries of lib/deformation_graph_point.py:181-191 (use_f64=1 evaluates in fp64 like SciPy).
  * Q[B,N,3], R[B,M,3] -> idx int64[B,N,k] (or idx32 int32, either may be NULL), d2 f32[B,N,k] (NULL ok;
  * with use_f64 the squared distance is rounded to fp32 on output, d2_f64 receives the fp64 value).
+ * ws (dvm_knn3_workspace_bytes) enables the uniform-grid search (O(N) work, bit-identical results); with
+ * ws == NULL, or for reference clouds below 1024 points, the shared-memory-tiled brute-force sweep runs.
  * ------------------------------------------------------------------------------------------ */
+size_t dvm_knn3_workspace_bytes(int B, int N, int M);
 int dvm_knn3(const float* Q, const float* R, int B, int N, int M, int k, int use_f64,
-             int64_t* idx, int32_t* idx32, float* d2, double* d2_f64, void* stream);
+             int64_t* idx, int32_t* idx32, float* d2, double* d2_f64, void* ws, size_t ws_bytes, void* stream);
 
 /* chamfer_3DDist forward/backward (ThibaultGROUEIX/ChamferDistancePytorch chamfer3D, call sites
  * models/loss.py:1099,1223 and 750,874): squared distances, int32 arg-mins, both directions. */
+size_t dvm_chamfer_workspace_bytes(int B, int N, int M);
 int dvm_chamfer_fwd(const float* a, const float* b, int B, int N, int M,
-                    float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* stream);
+                    float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* ws, size_t ws_bytes, void* stream);
 /* da[B,N,3], db[B,M,3] are OVERWRITTEN. */
 int dvm_chamfer_bwd(const float* a, const float* b, const int32_t* idx1, const int32_t* idx2,
                     const float* g1, const float* g2, int B, int N, int M,

@@ -44,8 +44,10 @@ def test_ctypes_binding_covers_header(lib_path):
     assert lib.dvm_fps_workspace_bytes(2, 50000) >= 2 * 50000 * 4
     rc = lib.dvm_softmap_fwd(None, None, None, 1, 8, 8, 8, 0, 1.0, 10, 1, 0, None, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"non-null" in lib.dvm_last_error_string()
-    rc = lib.dvm_knn3(None, None, 1, 8, 8, 3, 0, None, None, None, None, None)
+    rc = lib.dvm_knn3(None, None, 1, 8, 8, 3, 0, None, None, None, None, None, 0, None)
     assert rc == -1
+    assert lib.dvm_knn3_workspace_bytes(2, 5000, 5000) > 0 and lib.dvm_knn3_workspace_bytes(2, 5000, 500) == 0
+    assert lib.dvm_chamfer_workspace_bytes(1, 4995, 2200) == lib.dvm_knn3_workspace_bytes(1, 2200, 4995)
 
 
 def test_only_sm100a_code_is_embedded(lib_path):

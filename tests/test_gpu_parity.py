@@ -153,6 +153,79 @@ def test_knn3_large_uses_one_lane_path():
     assert torch.equal(idx.cpu()[:, sel], og.knn_exact(q[:, sel], r, 3)[0])
 
 
+@pytest.mark.parametrize("shape", [(2, 5000, 5000), (1, 4995, 2200), (1, 2200, 4995), (3, 1500, 1024)])
+def test_knn3_grid_equals_brute_force(shape):
+    """The uniform-grid search must reproduce the brute-force sweep bit for bit (indices AND distances),
+    for fp32 (k = 1, 3, 10) and fp64 (k = 2, 9) evaluation, with queries inside and far outside the grid."""
+    ops = _ops()
+    from dv_matcher_b200 import synthetic
+    B, N, M = shape
+    d = synthetic.make_batch(B, max(N, M), max(N, M), first_pair=3)
+    q = d["xyz1"][:, :N].clone()
+    r = d["xyz2"][:, :M].clone()
+    q[:, : N // 8] = q[:, : N // 8] * 3.0 + 0.7            # a slab of queries well outside the reference box
+    r[:, 5] = r[:, 4]                                      # exact duplicates -> index tie-break
+    r[:, 6] = r[:, 4]
+    qc, rc = _cuda(q), _cuda(r)
+    for k, f64 in ((1, False), (3, False), (10, False), (2, True), (9, True)):
+        ig, dg = ops.knn3(qc, rc, k, f64=f64, want_d2=True)
+        ib, db = ops.knn3(qc, rc, k, f64=f64, want_d2=True, algo="brute")
+        assert torch.equal(ig, ib), (shape, k, f64)
+        assert torch.equal(dg, db), (shape, k, f64)
+    # self k-NN (the xyz 10-NN of models/loss.py:1229): self first unless an exact duplicate has a lower index
+    ig = ops.knn3(rc, rc, 10)
+    ib = ops.knn3(rc, rc, 10, algo="brute")
+    assert torch.equal(ig, ib)
+    # Chamfer through the grid == brute force == oracle
+    g = ops.chamfer_fwd(qc, rc)
+    bf = ops.chamfer_fwd(qc, rc, algo="brute")
+    for x, y in zip(g, bf):
+        assert torch.equal(x, y)
+    r1, r2, j1, j2 = og.chamfer_3d(q, r)
+    assert torch.equal(g[2].cpu().long(), j1.long()) and torch.equal(g[3].cpu().long(), j2.long())
+    assert torch.equal(g[0].cpu(), r1) and torch.equal(g[1].cpu(), r2)
+
+
+def test_knn3_grid_degenerate_clouds():
+    """Flat, collinear and coincident reference clouds (zero-volume boxes) and k close to M."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(11)
+    M = 2048
+    flat = torch.rand(1, M, 3, generator=gen); flat[..., 2] = 0.25
+    line = torch.zeros(1, M, 3); line[..., 0] = torch.rand(1, M, generator=gen)
+    same = torch.full((1, M, 3), 0.5)
+    q = torch.rand(1, 777, 3, generator=gen) * 2 - 0.5
+    for r in (flat, line, same):
+        for k in (1, 10, 16):
+            a = ops.knn3(_cuda(q), _cuda(r), k, want_d2=True)
+            b = ops.knn3(_cuda(q), _cuda(r), k, want_d2=True, algo="brute")
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_knn3_grid_50k_properties():
+    """BASELINE size (N = M = 50k): grid result checked against brute force on a row sample and through
+    size-independent properties (self is its own nearest neighbour, ascending distances, symmetry of the
+    Chamfer arg-min relation)."""
+    ops = _ops()
+    from dv_matcher_b200 import synthetic
+    d = synthetic.make_batch(1, 50000, 50000, first_pair=1)
+    a, b = _cuda(d["xyz1"]), _cuda(d["xyz2"])
+    idx, d2 = ops.knn3(a, a, 10, want_d2=True)
+    assert torch.equal(idx[0, :, 0].cpu(), torch.arange(50000))
+    assert (d2[..., 1:] >= d2[..., :-1]).all()
+    rows = torch.randperm(50000, generator=torch.Generator().manual_seed(5))[:2000]
+    ib, db = ops.knn3(a[:, rows.cuda()], a, 10, want_d2=True, algo="brute")
+    assert torch.equal(idx[0, rows.cuda()], ib[0]) and torch.equal(d2[0, rows.cuda()], db[0])
+    d1, d2c, i1, i2 = ops.chamfer_fwd(a, b)
+    e1, e2, j1, j2 = ops.chamfer_fwd(a[:, rows.cuda()], b, algo="brute")
+    assert torch.equal(i1[0, rows.cuda()], j1[0]) and torch.equal(d1[0, rows.cuda()], e1[0])
+    # d1[i] is attained at i1[i]
+    pa, pb = d["xyz1"][0], d["xyz2"][0]
+    diff = pa - pb[i1[0].cpu().long()]
+    ref = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]
+    assert torch.equal(d1[0].cpu(), ref)
+
+
 def test_chamfer_fwd_bwd():
     ops = _ops()
     gen = torch.Generator().manual_seed(5)
