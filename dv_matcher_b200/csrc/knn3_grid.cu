@@ -214,6 +214,26 @@ grid_scatter_kernel(const float* __restrict__ R, int M, int stride, const int* _
     sorted[(size_t)b * M + pos] = make_float4(p[0], p[1], p[2], __int_as_float(i));
 }
 
+// occupied x-extent of every (z, y) row of cells: rowx[row] = (first, last) non-empty cell, (1, 0) when the row is
+// empty.  ny * nz entries per cloud -- small enough to stay in L1, so that the (mostly empty) rows a far query walks
+// through are rejected without touching the cell-start array in L2.
+__global__ void __launch_bounds__(GRID_THREADS)
+grid_rowinfo_kernel(const GridHeader* __restrict__ hdr, int stride, const int* __restrict__ start, int2* __restrict__ rowx) {
+    const int b = blockIdx.y;
+    const GridHeader g = hdr[b];
+    const int row = blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (row >= g.ny * g.nz) return;
+    const int* st = start + (size_t)b * stride + (size_t)row * g.nx;
+    int lo = 1, hi = 0;
+    int prev = st[0];
+    for (int x = 0; x < g.nx; ++x) {
+        const int nxt = st[x + 1];
+        if (nxt != prev) { if (hi < lo) lo = x; hi = x; }
+        prev = nxt;
+    }
+    rowx[(size_t)b * stride + row] = make_int2(lo, hi);
+}
+
 template <typename T> struct GDist;
 template <> struct GDist<float> {
     static __device__ __forceinline__ float eval(float qx, float qy, float qz, float4 p) {
@@ -264,14 +284,15 @@ __device__ __forceinline__ void scan_span(GList<T, K>& list, const float4* __res
 template <typename T, int K, int GRID_LPQ>
 __global__ void __launch_bounds__(GRID_THREADS)
 knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHeader* __restrict__ hdr, int stride,
-                 const int* __restrict__ start, const int* __restrict__ cstart, const float4* __restrict__ sorted,
-                 int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ d2f, double* __restrict__ d2d) {
+                 const int* __restrict__ start, const int* __restrict__ cstart, const int2* __restrict__ rowx_all,
+                 const float4* __restrict__ sorted, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ d2f, double* __restrict__ d2d) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * (GRID_THREADS / GRID_LPQ) + threadIdx.x / GRID_LPQ;
     const int sub = threadIdx.x % GRID_LPQ;
     const bool live = q < N;
     const GridHeader g = hdr[b];
     const int* st = start + (size_t)b * stride;
+    const int2* rowx = rowx_all + (size_t)b * stride;
     const float4* pts = sorted + (size_t)b * M;
     float qx = g.x0, qy = g.y0, qz = g.z0;
     if (live) {
@@ -293,6 +314,7 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
     // the loop in lock step (the step decisions are team-uniform).
     int sp = -1, s = GRID_LPQ > 1 ? 1 : 0;
     bool coarse_done = false;
+    T team_ub = (T)INFINITY;          // upper bound of the team's k-th distance: min over lanes that know k points
     for (;;) {
         const int zlo = max(cz - s, 0), zhi = min(cz + s, g.nz - 1);
         const int ylo = max(cy - s, 0), yhi = min(cy + s, g.ny - 1);
@@ -301,14 +323,36 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
         const int nrows = (zhi - zlo + 1) * wy;
         for (int r = sub; r < nrows; r += GRID_LPQ) {
             const int z = zlo + r / wy, y = ylo + r % wy;
+            const int2 ext = __ldg(rowx + z * g.ny + y);       // occupied cells of the row (L1-resident table)
+            int x0 = max(xlo, ext.x), x1 = min(xhi, ext.y);
+            if (x0 > x1) continue;                             // nothing of the row inside the box
+            // ball pruning with the lane's own k-th distance (an upper bound of the final one): a row whose (y, z)
+            // slab is farther than that is skipped, the others are clipped to the chord of the ball.  Margins keep
+            // every point that could tie (equal distance, lower index) inside.
+            T kth_l = team_ub;
+#pragma unroll
+            for (int t = 0; t < K; ++t) if (t == k - 1) kth_l = list.key[t] < kth_l ? list.key[t] : kth_l;
+            if (kth_l < (T)INFINITY) {
+                const float ylo_f = g.y0 + (float)y * g.h, zlo_f = g.z0 + (float)z * g.h;
+                const float dy = fmaxf(fmaxf(ylo_f - qy, qy - (ylo_f + g.h)) - margin, 0.f);
+                const float dz = fmaxf(fmaxf(zlo_f - qz, qz - (zlo_f + g.h)) - margin, 0.f);
+                const float lb2 = (dy * dy + dz * dz) * (1.f - 1e-5f);
+                const float best = (float)kth_l * (1.f + 1e-5f) + 1e-30f;
+                if (lb2 > best) continue;
+                const float rx = sqrtf(best - lb2) * (1.f + 1e-5f) + margin;
+                const float fa = (qx - rx - g.x0) * g.inv_h - 1.f, fb = (qx + rx - g.x0) * g.inv_h + 1.f;
+                if (fa > (float)x0) x0 = (int)fminf(fa, 4e6f);
+                if (fb < (float)x1) x1 = (int)fmaxf(fb, -1.f);
+                if (x0 > x1) continue;
+            }
             const int row = (z * g.ny + y) * g.nx;
             if (z >= cz - sp && z <= cz + sp && y >= cy - sp && y <= cy + sp) {   // row crossed the old box: two end spans
-                const int l1 = cx - sp - 1;                // left span  [xlo, l1]
-                if (l1 >= xlo) scan_span<T, K>(list, pts, st[row + xlo], st[row + l1 + 1], qx, qy, qz);
-                const int r0 = cx + sp + 1;                // right span [r0, xhi]
-                if (r0 <= xhi) scan_span<T, K>(list, pts, st[row + r0], st[row + xhi + 1], qx, qy, qz);
+                const int l1 = min(cx - sp - 1, x1);          // left span  [x0, l1]
+                if (l1 >= x0) scan_span<T, K>(list, pts, st[row + x0], st[row + l1 + 1], qx, qy, qz);
+                const int r0 = max(cx + sp + 1, x0);          // right span [r0, x1]
+                if (r0 <= x1) scan_span<T, K>(list, pts, st[row + r0], st[row + x1 + 1], qx, qy, qz);
             } else {
-                scan_span<T, K>(list, pts, st[row + xlo], st[row + xhi + 1], qx, qy, qz);
+                scan_span<T, K>(list, pts, st[row + x0], st[row + x1 + 1], qx, qy, qz);
             }
         }
         sp = s;
@@ -330,6 +374,7 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
         for (int t = 0; t < K; ++t) {
             n_safe += list.key[t] < safe ? 1 : 0;
             if (list.key[t] < (T)INFINITY) { ++n_known; far = list.key[t]; }
+            if (t == k - 1 && list.key[t] < team_ub) team_ub = list.key[t];
         }
 #pragma unroll
         for (int o = GRID_LPQ / 2; o > 0; o >>= 1) {
@@ -337,8 +382,11 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
             n_known += __shfl_xor_sync(full, n_known, o);
             const T of = __shfl_xor_sync(full, far, o);
             far = of > far ? of : far;
+            const T ou = __shfl_xor_sync(full, team_ub, o);
+            team_ub = ou < team_ub ? ou : team_ub;
         }
         if (n_safe >= k) break;
+        if (team_ub < (T)INFINITY) far = team_ub;
         if (n_known >= k) {
             // half-width whose box contains the ball of radius sqrt(far) around q (q may sit anywhere in its cell,
             // or outside the grid next to it)
@@ -402,7 +450,7 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct GridWs { GridHeader* hdr; int* start; int* cursor; int* cstart; int* cell_of; float4* sorted; int* bsum; int stride; int ncell_max; int nblk_max; };
+struct GridWs { GridHeader* hdr; int* start; int* cursor; int* cstart; int* cell_of; float4* sorted; int* bsum; int2* rowx; int stride; int ncell_max; int nblk_max; };
 
 static size_t grid_ws_layout(void* base, size_t cap, int B, int M, GridWs* out) {
     GridWs w{};
@@ -419,6 +467,7 @@ static size_t grid_ws_layout(void* base, size_t cap, int B, int M, GridWs* out) 
     w.sorted = ws.take<float4>((size_t)B * M);
     w.nblk_max = ceil_div(w.ncell_max > GRID_COARSE_MAX ? w.ncell_max : GRID_COARSE_MAX, SCAN_BLOCK);
     w.bsum = ws.take<int>((size_t)2 * B * w.nblk_max);
+    w.rowx = ws.take<int2>((size_t)B * w.stride);
     if (out) *out = w;
     return align_up(ws.off, 256);
 }
@@ -429,7 +478,7 @@ template <typename T, int K, int LPQ = 1>
 static void launch_query(const float* Q, int B, int N, int M, int k, const GridWs& w,
                          int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, cudaStream_t st) {
     dim3 grid(ceil_div(N, GRID_THREADS / LPQ), B);
-    knn3_grid_kernel<T, K, LPQ><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.sorted, idx64, idx32, d2f, d2d);
+    knn3_grid_kernel<T, K, LPQ><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, idx64, idx32, d2f, d2d);
 }
 
 // k nearest neighbours of Q[B,N,3] in R[B,M,3] through a grid built on R (inside ws)
@@ -453,6 +502,8 @@ int launch_knn3_grid(const float* Q, const float* R, int B, int N, int M, int k,
     grid_scan_c_kernel<<<dim3(w.nblk_max, B, 2), 1024, 0, st>>>(sa, B);
     DVM_LAUNCH_CHECK();
     grid_scatter_kernel<<<gp, GRID_THREADS, 0, st>>>(R, M, w.stride, w.cell_of, w.cursor, w.sorted);
+    DVM_LAUNCH_CHECK();
+    grid_rowinfo_kernel<<<dim3(ceil_div(w.ncell_max, GRID_THREADS), B), GRID_THREADS, 0, st>>>(w.hdr, w.stride, w.start, w.rowx);
     DVM_LAUNCH_CHECK();
 #define DVM_GRID_DISPATCH(T)                                                                         \
     if (k == 1)       launch_query<T, 1, 8>(Q, B, N, M, k, w, idx64, idx32, d2f, d2d, st);            \
