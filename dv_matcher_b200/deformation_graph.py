@@ -172,6 +172,11 @@ def deformation_graph_node(verts1):
     return g.nodes_idx.to(verts1.dtype if verts1.dtype.is_floating_point else torch.float32), dg_list
 
 
+def deformation_graph_node_list(verts1):
+    """Same as `deformation_graph_node`; the name the entry scripts' local copies are rebound to (deform.py:41-53)."""
+    return deformation_graph_node(verts1)
+
+
 class _LazyNumpy:
     """Device tensor that turns into the reference's numpy array only if somebody asks (no sync otherwise)."""
 

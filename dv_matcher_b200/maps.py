@@ -160,8 +160,13 @@ class LazySoftMap(_MapBase):
         self._sparse = None
 
     def topk(self, k=TOPK, prec=None):
+        if prec is None:
+            # the backward re-uses the forward's row statistics: training takes the fp32 candidate pass (1e-4 parity
+            # of weights AND gradients) unless DVM_TRAIN_PREC says otherwise; inference keeps the tcgen05 pass
+            needs_grad = torch.is_grad_enabled() and (self.x.requires_grad or self.y.requires_grad)
+            prec = os.environ.get("DVM_TRAIN_PREC", "fp32") if needs_grad else _PRECISION
         w, idx, argmin, top_d, rmin, rsum = _SoftMapTopK.apply(self.x.float().contiguous(), self.y.float().contiguous(),
-                                                              self.alpha, k, prec or _PRECISION)
+                                                              self.alpha, k, prec)
         return SparseSoftMap(idx, w, self.shape[2], argmin, top_d, rmin, rsum)
 
     def sparse(self):

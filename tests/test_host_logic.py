@@ -1,0 +1,104 @@
+"""CPU-only tests of the host-side logic: install() name rebinding, pair sharding and the one-bucket gradient
+all-reduce over gloo with world_size = 2 (the N > 1 path of SURVEY 8e), sparse-map tensor protocol."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_install_rebinds_and_restores():
+    from dv_matcher_b200 import install as inst, maps, geometry, losses
+    fake = types.ModuleType("models.loss")
+    for n in ("knnsearch_t", "knnsearch_t_grad", "knn_grad", "index_points", "GraphDeformLoss_Neural", "dist_chamfer_3D"):
+        setattr(fake, n, object())
+    fake.unrelated = 42
+    script = types.ModuleType("deform")
+    script.knnsearch_t = script.topk_pi = object()
+    pkg = types.ModuleType("models")
+    saved = {k: sys.modules.get(k) for k in ("models", "models.loss", "deform")}
+    sys.modules.update({"models": pkg, "models.loss": fake, "deform": script})
+    try:
+        done = inst.install(import_missing=False)
+        assert done["models.loss"] == 6 and done["deform"] == 2
+        assert fake.knnsearch_t is maps.knnsearch_t and fake.knn_grad is geometry.knn_grad
+        assert fake.GraphDeformLoss_Neural is losses.GraphDeformLoss_Neural and fake.unrelated == 42
+        assert script.knnsearch_t is maps.knnsearch_t_1based and script.topk_pi is maps.topk_pi
+        inst.uninstall()
+        assert not (fake.knnsearch_t is maps.knnsearch_t)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_shard_pairs_partition():
+    from dv_matcher_b200.distributed import shard_pairs
+    for n in (0, 1, 7, 16):
+        for world in (1, 2, 8):
+            got = sorted(i for r in range(world) for i in shard_pairs(n, r, world))
+            assert got == list(range(n))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from dv_matcher_b200 import distributed as dd
+    r, w, dev = dd.init(backend="gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ELU(), torch.nn.Linear(5, 3))
+    data = torch.arange(4 * 6, dtype=torch.float32).reshape(4, 6) / 10.0
+    mine = data[dd.shard_pairs(4, r, w)]
+    net(mine).pow(2).sum().backward()
+    frozen = list(net.parameters())[-1]
+    if r == 1:
+        frozen.grad = None                           # a rank without a gradient for one tensor contributes zeros
+    bucket = dd.allreduce_gradients(list(net.parameters()), world=w)
+    res = [p.grad.clone() for p in net.parameters()]
+    gathered = dd.gather_pair_results({"rank": r, "pairs": dd.shard_pairs(4, r, w)}, world=w)
+    if r == 0:
+        torch.save(dict(grads=res, n=bucket.numel(), gathered=gathered), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo_world2(tmp_path):
+    out = str(tmp_path / "res.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    # single-process reference: mean over the two shards' gradient sums
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ELU(), torch.nn.Linear(5, 3))
+    data = torch.arange(4 * 6, dtype=torch.float32).reshape(4, 6) / 10.0
+    grads = []
+    for r in range(2):
+        net.zero_grad()
+        net(data[r::2]).pow(2).sum().backward()
+        gs = [p.grad.clone() for p in net.parameters()]
+        if r == 1:
+            gs[-1] = torch.zeros_like(gs[-1])
+        grads.append(gs)
+    for a, b0, b1 in zip(got["grads"], grads[0], grads[1]):
+        assert torch.allclose(a, (b0 + b1) / 2, rtol=1e-6, atol=1e-7)
+    assert got["n"] == sum(p.numel() for p in net.parameters())
+    assert [g["pairs"] for g in got["gathered"]] == [[0, 2], [1, 3]]
+
+
+def test_sparse_soft_map_protocol_cpu():
+    """SparseSoftMap's dense view and torch-function interception (no kernels: dense fallback for foreign shapes)."""
+    from dv_matcher_b200.maps import SparseSoftMap, topk_pi
+    a = torch.rand(2, 5, 12)
+    sm = topk_pi(a, k=3)
+    assert isinstance(sm, SparseSoftMap) and tuple(sm.shape) == (2, 5, 12)
+    dense = sm.to_dense()
+    vals, idx = torch.topk(a, 3, dim=-1)
+    assert torch.equal(dense, torch.zeros_like(a).scatter(-1, idx, vals))
+    assert torch.equal(sm.transpose(1, 2), dense.transpose(1, 2)) and sm.dim() == 3 and sm.size(2) == 12
