@@ -254,8 +254,8 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("n") == n and tj.get("pairs") == B and tj.get("prec") == args.prec:
-            traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("n") == n and tj.get("prec") == args.prec:          # ncu capture of the same kernel / size: scale to this launch
+            traffic = tj.get("dram_bytes_per_problem", 0) * 2 * B or None
     e2e = main["e2e"]
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
