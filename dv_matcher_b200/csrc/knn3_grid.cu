@@ -281,13 +281,15 @@ __device__ __forceinline__ void scan_span(GList<T, K>& list, const float4* __res
 // the end.  8 for Chamfer (k = 1: queries are typically OFF the reference surface and walk hundreds of mostly
 // empty rows -> 8 independent chains of dependent loads), 1 for the self / node k-NN (queries on the surface).
 
-template <typename T, int K, int GRID_LPQ>
+// kSelf: Q is the reference cloud itself -> thread t handles the t-th point in CELL-SORTED order, so the lanes of a
+// warp are spatial neighbours (same rows, same spans: little divergence, L1-friendly) and write to their original row.
+template <typename T, int K, int GRID_LPQ, bool kSelf>
 __global__ void __launch_bounds__(GRID_THREADS)
 knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHeader* __restrict__ hdr, int stride,
                  const int* __restrict__ start, const int* __restrict__ cstart, const int2* __restrict__ rowx_all,
                  const float4* __restrict__ sorted, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ d2f, double* __restrict__ d2d) {
     const int b = blockIdx.y;
-    const int q = blockIdx.x * (GRID_THREADS / GRID_LPQ) + threadIdx.x / GRID_LPQ;
+    int q = blockIdx.x * (GRID_THREADS / GRID_LPQ) + threadIdx.x / GRID_LPQ;
     const int sub = threadIdx.x % GRID_LPQ;
     const bool live = q < N;
     const GridHeader g = hdr[b];
@@ -296,8 +298,13 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
     const float4* pts = sorted + (size_t)b * M;
     float qx = g.x0, qy = g.y0, qz = g.z0;
     if (live) {
-        const float* qp = Q + ((size_t)b * N + q) * 3;
-        qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
+        if (kSelf) {
+            const float4 p = __ldg(pts + q);
+            qx = p.x; qy = p.y; qz = p.z; q = __float_as_int(p.w);
+        } else {
+            const float* qp = Q + ((size_t)b * N + q) * 3;
+            qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
+        }
     }
     const int cx = cell_coord(qx, g.x0, g.inv_h, g.nx), cy = cell_coord(qy, g.y0, g.inv_h, g.ny), cz = cell_coord(qz, g.z0, g.inv_h, g.nz);
     GList<T, K> list;
@@ -475,10 +482,11 @@ static size_t grid_ws_layout(void* base, size_t cap, int B, int M, GridWs* out) 
 size_t knn3_grid_workspace_bytes(int B, int M) { return grid_ws_layout(nullptr, 0, B, M, nullptr); }
 
 template <typename T, int K, int LPQ = 1>
-static void launch_query(const float* Q, int B, int N, int M, int k, const GridWs& w,
+static void launch_query(const float* Q, bool self, int B, int N, int M, int k, const GridWs& w,
                          int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, cudaStream_t st) {
     dim3 grid(ceil_div(N, GRID_THREADS / LPQ), B);
-    knn3_grid_kernel<T, K, LPQ><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, idx64, idx32, d2f, d2d);
+    if (self) knn3_grid_kernel<T, K, LPQ, true><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, idx64, idx32, d2f, d2d);
+    else      knn3_grid_kernel<T, K, LPQ, false><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, idx64, idx32, d2f, d2d);
 }
 
 // k nearest neighbours of Q[B,N,3] in R[B,M,3] through a grid built on R (inside ws)
@@ -505,11 +513,12 @@ int launch_knn3_grid(const float* Q, const float* R, int B, int N, int M, int k,
     DVM_LAUNCH_CHECK();
     grid_rowinfo_kernel<<<dim3(ceil_div(w.ncell_max, GRID_THREADS), B), GRID_THREADS, 0, st>>>(w.hdr, w.stride, w.start, w.rowx);
     DVM_LAUNCH_CHECK();
+    const bool self = (Q == R) && (N == M);
 #define DVM_GRID_DISPATCH(T)                                                                         \
-    if (k == 1)       launch_query<T, 1, 8>(Q, B, N, M, k, w, idx64, idx32, d2f, d2d, st);            \
-    else if (k <= 4)  launch_query<T, 4>(Q, B, N, M, k, w, idx64, idx32, d2f, d2d, st);               \
-    else if (k <= 10) launch_query<T, 10>(Q, B, N, M, k, w, idx64, idx32, d2f, d2d, st);              \
-    else              launch_query<T, 16>(Q, B, N, M, k, w, idx64, idx32, d2f, d2d, st);
+    if (k == 1)       launch_query<T, 1, 8>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);            \
+    else if (k <= 4)  launch_query<T, 4>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);               \
+    else if (k <= 10) launch_query<T, 10>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);              \
+    else              launch_query<T, 16>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);
     if (f64) { DVM_GRID_DISPATCH(double) } else { DVM_GRID_DISPATCH(float) }
 #undef DVM_GRID_DISPATCH
     DVM_LAUNCH_CHECK();

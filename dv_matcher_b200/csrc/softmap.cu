@@ -753,9 +753,10 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     // when it has nothing to do): threshold scan + exact emit; what even that cannot settle (> RESC_CAP columns
     // inside the threshold, or > RESC_MAX flagged rows) goes to the fp32 candidate pass.
     {
-        int nch = ceil_div(2 * kNumSM, B);
+        // column chunks of ~192 columns: a chunk of Y (96 KB at C = 128) stays in L1 while the CTA walks its flagged rows
+        int nch = ceil_div(M, 192);
         if (nch > RESC_NCH_MAX) nch = RESC_NCH_MAX;
-        if (nch > ceil_div(M, 64)) nch = ceil_div(M, 64);
+        if (nch < 1) nch = 1;
         const int chunk = ceil_div(M, nch);
         nch = ceil_div(M, chunk);
         const float a2 = alpha * kLog2e;

@@ -185,14 +185,24 @@ tc_prep_kernel(const float* __restrict__ src, int rows_per_b, int rows_alloc, in
     }
     const float* s = src + ((size_t)b * rows_per_b + r) * C;
     float n2 = 0.f, e2 = 0.f;
-    for (int c = lane; c < Cpad; c += 32) {
-        const float v = c < C ? __ldg(s + c) : 0.f;
-        float vr;
-        uint16_t bits = Cvt16<kBF16>::bits(kIsY ? -v : v, vr);
-        d[c] = bits;
-        n2 = fmaf(vr, vr, n2);
-        const float e = (kIsY ? -v : v) - vr;      // +-inf when the value overflows the 16-bit format
-        e2 = fmaf(e, e, e2);
+    for (int c = lane * 4; c < Cpad; c += 128) {             // C % 4 == 0: float4 in, 4 x 16-bit (8 bytes) out
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C) v = __ldg(reinterpret_cast<const float4*>(s + c));
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        uint16_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float x = kIsY ? -in[t] : in[t];
+            float vr;
+            o[t] = Cvt16<kBF16>::bits(x, vr);
+            n2 = fmaf(vr, vr, n2);
+            const float e = x - vr;                          // +-inf when the value overflows the 16-bit format
+            e2 = fmaf(e, e, e2);
+        }
+        uint2 pk;
+        pk.x = (uint32_t)o[0] | ((uint32_t)o[1] << 16);
+        pk.y = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
+        *reinterpret_cast<uint2*>(d + c) = pk;
     }
     n2 = warp_sum(n2); e2 = warp_sum(e2);
     if (lane < TC_KEXT) {
