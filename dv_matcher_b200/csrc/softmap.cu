@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
     if (lane == 0) {
         float bound = 0.f, e2 = 0.f;
         if (a.err_x) bound = a.err_x[g] + a.err_ymax[b];
-        if (a.tc_xx) e2 = 2e-6f * (a.tc_xx[g] + a.tc_yymax[b]);
+        if (a.tc_xx) e2 = 4e-6f * (a.tc_xx[g] + a.tc_yymax[b]);      // MMA accumulation + 16 ulp of packed list keys
         bool ok;
         if (key16 == INFINITY) ok = bound < INFINITY;            // every column is in the list (M < KC) unless the
         else {                                                   // 16-bit conversion overflowed

@@ -28,15 +28,14 @@ constexpr int TC_BM = 2 * TC_SUB;     // rows per CTA
 constexpr int TC_BN = 128;            // columns per tile (UMMA N)
 constexpr int TC_KBLK = 64;           // 16-bit elements per 128-byte swizzle row
 constexpr int TC_KEXT = 16;           // extra K block: norm columns (one UMMA K step), 32-byte swizzle rows
-constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_SCAN_WARPS = 16;      // epilogue scanners
+constexpr int TC_CONS_WARPS = 8;       // epilogue consumers (one per 32 rows: sub-block x TMEM lane quarter)
+constexpr int TC_THREADS = 64 + 32 * (TC_SCAN_WARPS + TC_CONS_WARPS);
 constexpr int TC_NST = 2;             // Y ring depth
 constexpr int TC_BLK_BYTES = 128 * 128;        // one 128-row x 64-element K block
 constexpr int TC_EXT_BYTES = 128 * 32;         // one 128-row x 16-element K block
-constexpr int TC_MAX_SPLIT = P_MAX / 2;
+constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_CHUNK = 16;               // columns per min-tree
-constexpr int TC_FLUSH_AT = 4;             // flush the pending buffers when any lane holds more than this
-constexpr int TC_CAP = TC_FLUSH_AT + TC_CHUNK;   // slots per lane: a chunk can append at most TC_CHUNK entries
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int TC_PRIME_STRIDE = 16;        // priming pass: every 16th tile
 constexpr int TC_PRIME_MIN_TILES = 128;     // ... when the sweep has at least this many tiles (M >= 16k)
@@ -246,128 +245,84 @@ struct TcParams {
     const float* xx;             // [B*N]
     unsigned* thr_global;        // [B*N] per-row list threshold (true d^2 bits): written by the priming pass, refined
                                  // with atomicMin by the sweep
+    unsigned* rmin_global;       // [B*N] smallest sampled d^2 of the row (priming pass): initial softmax reference
     CandBuffers cb;
 };
 
-// Epilogue candidate handling (per thread = one row, 64 columns of every tile):
-//   * the K best (key, idx) of the row live in REGISTERS as a sorted list;
-//   * per 16-column chunk a min-tree yields the chunk minimum; if it is below the row's "interesting" bound
-//     thr_hi = max(list threshold, softmax-window bound) the lane appends the interesting entries of the chunk
-//     to its pending buffer in shared memory (slot-major [slot][lane] -> conflict-free);
-//   * when any lane holds more than TC_FLUSH_AT entries the whole warp flushes: every lane inserts ITS OWN
-//     pending entries into its register list simultaneously (lane-parallel, ~10x cheaper than one divergent
-//     insertion per hit); evicted / rejected entries go to the row's softmax mass;
-//   * the list threshold of a row starts from the PRIMING pass (the 6th smallest key of a 1/32 column sample,
-//     i.e. roughly the 150th best of the row -- no "everything is a hit" start-up phase, ~4x fewer insertions)
-//     and is shared between the row's partial lists: the two column halves of a CTA via shared memory,
-//     column-split CTAs via atomicMin in global memory.  Whatever the threshold was, every column a partial
-//     list discarded has a key >= the list's final threshold, which is handed to finalize as the discard bound
-//     `t` -- so a threshold that turns out too tight costs a rescue scan, never a wrong answer.
+// Epilogue = SCANNER warps + CONSUMER warps.
+//
+// 16 scanner warps (TMEM lane quarter = warp % 4; (sub-block, column half) from the warp's group of four): one
+// thread = one row x 64 columns of every tile, read with software-pipelined tcgen05.ld.  Per 16-column chunk a
+// min-tree (8 three-input min instructions) gives the chunk minimum; if it is below the row's published bound thr_hi
+// the lane copies the WHOLE chunk (16 keys, row, first column) into its consumer's queue in shared memory -- ~20
+// uniform instructions per warp and chunk, no per-entry work, no per-thread lists.  Scanner cost is therefore almost
+// independent of the data.
+//
+// 8 consumer warps (one per 32 rows = sub-block x TMEM lane quarter) drain the queues with ONE LANE PER QUEUE ENTRY
+// (full lane utilisation whatever the rows are): the entry's keys below the bound replace the worst entry of the
+// row's K-entry list (shared memory) or add their softmax term exp2(-a2 (d - r)) to the row's mass; the lane then
+// publishes the row's new bound thr_hi = max(list threshold, softmax-window bound).  Entries of the same row inside
+// one batch of 32 are serialised in queue order (__match_any_sync).  The queue is a ring with a release/acquire
+// sequence word per slot; producers reserve slots with one warp-aggregated atomicAdd and wait for space, the
+// consumer never waits for a producer, so the protocol cannot deadlock.
+//
+// The list threshold of a row starts from the PRIMING pass (8th smallest key of a 1/16 column sample ~ rank 130) and
+// is shared between column-split CTAs via atomicMin in global memory.  Whatever the thresholds were, every column a
+// list discarded has key >= the list's final threshold, which finalize receives as the discard bound `t`.
 // Keys live in the half domain  key = (d~^2 - |x~|^2) / 2.
-constexpr int KP = 6;             // list length of the priming pass
+constexpr int KP = 8;                  // list length of the priming pass
+constexpr int Q_CAP = 64;              // queue slots per consumer
+constexpr int Q_ENTRY = 80;            // bytes: 16 keys | row, first column | sequence word, pad
+constexpr int LIST_STRIDE = KC + 1;    // float2 per row (odd stride in 8-byte units: conflict-poor)
+constexpr float LIST_EMPTY = 3.0e38f;  // "no entry" key (finite, so that a slot number can live in its low mantissa bits)
 
-template <int K>
-struct EpiState {
-    TopList<K> list;
-    float thr_list;        // append threshold: min(own K-th best, primed / published thresholds of the row)
-    float thr_mass;        // softmax window bound in the key domain (soft mode): entries in [thr_list, thr_mass) only add mass
-    float thr_hi;          // max(thr_list, thr_mass): anything below is appended to the pending buffer
-    float kr, r;           // smallest key seen so far by this thread (over ALL its columns) and its distance
-    float l;               // mass of the non-candidate columns relative to r
-    uint32_t wr;           // write cursor into the lane's pending buffer (shared-window address, 256 B per slot)
-};
+struct QCtl { unsigned tail, head, done, pad; };
 
 __device__ __forceinline__ float ex2_approx(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
-__device__ __forceinline__ float key_to_dist(float key, float xx) { return sqrtf(fmaxf(fmaf(2.f, key, xx), 0.f)); }
-
-// softmax term of a non-candidate column this thread has already swept (key >= st.kr, exponent <= ~0).  These
-// terms are all below the 16 exact ones, so MUFU-approximate sqrt / exp2 (2 ulp each) is ample.
-__device__ __forceinline__ float epi_term(float key, float xx, float r, float a2) {
+__device__ __forceinline__ float key_dist_approx(float key, float xx) {        // 2 ulp: fine for non-candidate terms
     const float x = fmaxf(fmaf(2.f, key, xx), 1e-30f);
-    const float d = x * __frsqrt_rn(x);
-    return ex2_approx(-a2 * (d - r));
+    return x * __frsqrt_rn(x);
 }
-
-// a chunk minimum below everything seen so far: move the reference point of the mass (rare: O(log M) times per
-// row).  r only has to be A reference distance used consistently for l, so the MUFU approximations are fine.
-template <int K>
-__device__ __forceinline__ void epi_new_min(EpiState<K>& st, float m, float xx, float a2, float coa) {
-    const float x = fmaxf(fmaf(2.f, m, xx), 1e-30f);
-    const float rn = x * __frsqrt_rn(x);
-    if (st.l != 0.f) st.l *= ex2_approx(-a2 * (st.r - rn));
-    st.kr = m; st.r = rn;
-    const float te = rn + coa;
-    st.thr_mass = 0.5f * (te * te - xx);
-    st.thr_hi = fmaxf(st.thr_list, st.thr_mass);
-}
-
-// lane-parallel flush of the pending buffers (warp-uniform trip count).  Per round every lane takes ITS next
-// pending entry: a list candidate is inserted (the sorted insertion only runs in rounds where some lane has
-// one), everything else -- and whatever an insertion evicts -- adds its softmax term.
-template <bool kSoft, int K>
-__device__ __forceinline__ void epi_flush(EpiState<K>& st, uint32_t buf_a, float xx, float a2) {
-    const int cnt = (int)((st.wr - buf_a) >> 8);
-    const int mx = __reduce_max_sync(kFull, cnt);
-#pragma unroll 1
-    for (int e = 0; e < mx; ++e) {
-        const bool active = e < cnt;
-        float2 kv = make_float2(INFINITY, 0.f);
-        if (active) kv = lds_v2(buf_a + e * 256);
-        const bool cand = kv.x < st.list.worst();
-        float out = kv.x;
-        if (__any_sync(kFull, cand)) {
-            if (cand) out = st.list.push(kv.x, __float_as_int(kv.y));
-        }
-        if (kSoft && out != INFINITY) st.l += epi_term(out, xx, st.r, a2);
-    }
-    st.wr = buf_a;
-    st.thr_list = fminf(st.thr_list, st.list.worst());
-    st.thr_hi = kSoft ? fmaxf(st.thr_list, st.thr_mass) : st.thr_list;
-}
-
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
-__device__ __forceinline__ float min4(float a, float b, float c, float d) { return fminf(fminf(a, b), fminf(c, d)); }
+__device__ __forceinline__ float min16(const float (&k)[16]) {                  // 8 three-input min instructions
+    return fminf(min3(min3(k[0], k[1], k[2]), min3(k[3], k[4], k[5]), min3(k[6], k[7], k[8])),
+                 min3(min3(k[9], k[10], k[11]), min3(k[12], k[13], k[14]), k[15]));
+}
+__device__ __forceinline__ unsigned lds_u32_volatile(uint32_t a) { unsigned r; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ unsigned lds_u32_acquire(uint32_t a) { unsigned r; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ void sts_u32_release(uint32_t a, unsigned v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+    float4 r; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory"); return r;
+}
 
-// one 16-column chunk of one row: min-tree, slow path (append interesting entries), flush when a buffer fills up
-template <bool kSoft, bool kPrime, int K>
-__device__ __forceinline__ void process_chunk(EpiState<K>& st, const float (&k)[TC_CHUNK], int cbase, uint32_t buf_a,
-                                              uint32_t thr_mine_a, uint32_t thr_other_a, unsigned* thr_g, bool row_ok,
-                                              float xx, const TcParams& p) {
-    // chunk minimum: 8 three-input min instructions
-    const float m = fminf(min3(min3(k[0], k[1], k[2]), min3(k[3], k[4], k[5]), min3(k[6], k[7], k[8])),
-                          min3(min3(k[9], k[10], k[11]), min3(k[12], k[13], k[14]), k[15]));
-    const bool slow = m < st.thr_hi;
-    if (__any_sync(kFull, slow)) {
-        if (slow) {
-            if (kSoft && m < st.kr) epi_new_min(st, m, xx, p.a2, p.cut_over_alpha);
-            const float th = st.thr_hi;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (min4(k[q * 4], k[q * 4 + 1], k[q * 4 + 2], k[q * 4 + 3]) < th) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (k[q * 4 + t] < th) {       // list candidate or softmax-window term: sorted out by the flush
-                            sts_v2(st.wr, k[q * 4 + t], __int_as_float(cbase + q * 4 + t));
-                            st.wr += 256;
-                        }
-                    }
-                }
-            }
-        }
-        if (__any_sync(kFull, st.wr > buf_a + TC_FLUSH_AT * 256)) {
-            epi_flush<kSoft>(st, buf_a, xx, p.a2);
-            if (!kPrime && row_ok) {
-                const float w = st.list.worst();
-                sts_f32(thr_mine_a, w);
-                const float t = lds_f32(thr_other_a);
-                if (t < st.thr_list) { st.thr_list = t; st.thr_hi = kSoft ? fmaxf(t, st.thr_mass) : t; }
-                if (p.multi_split && w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
-            }
-        }
+// scanner: one 16-column chunk of one row
+__device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase, uint32_t thr_hi_a, uint32_t q_a, uint32_t ctl_a,
+                                           int row_in_q, int lane) {
+    const float th = lds_f32(thr_hi_a);
+    const bool slow = min16(k) < th;
+    const unsigned mask = __ballot_sync(kFull, slow);
+    if (mask == 0u) return;                                          // warp-uniform
+    const int n = __popc(mask);
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned*>(__cvta_shared_to_generic(ctl_a)), (unsigned)n);   // QCtl::tail
+    base = __shfl_sync(kFull, base, 0);
+    while ((int)(base + (unsigned)n - lds_u32_volatile(ctl_a + 4)) > Q_CAP) __nanosleep(20);     // QCtl::head: wait for space
+    if (slow) {
+        const unsigned g = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+        const uint32_t ea = q_a + (g % Q_CAP) * Q_ENTRY;
+        sts_v4(ea, k[0], k[1], k[2], k[3]);
+        sts_v4(ea + 16, k[4], k[5], k[6], k[7]);
+        sts_v4(ea + 32, k[8], k[9], k[10], k[11]);
+        sts_v4(ea + 48, k[12], k[13], k[14], k[15]);
+        sts_v2(ea + 64, __int_as_float(row_in_q), __int_as_float(cbase));
+        sts_u32_release(ea + 72, g / Q_CAP + 1u);                    // publishes the entry
     }
 }
 
-// kPrime: priming pass -- strided tile sample, K = KP, hard mode, only output is thr_global.
+// kPrime: priming pass -- strided tile sample, K = KP, hard mode, only outputs are thr_global / rmin_global.
 template <bool kSoft, bool kPrime>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXe,
@@ -377,9 +332,18 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int unit = p.KB * TC_BLK_BYTES + TC_EXT_BYTES;  // one 128-row operand block, all of K
     uint8_t* Xs = smem;                                   // [2 sub-blocks][KB x 16 KB | 4 KB]
     uint8_t* Ys = Xs + 2 * unit;                          // [NST][KB x 16 KB | 4 KB]
-    float2* cand_buf = reinterpret_cast<float2*>(Ys + TC_NST * unit);                 // [16 warps][TC_CAP][32] (key, idx)
-    float* thr_sh = reinterpret_cast<float*>(cand_buf + TC_EPI_WARPS * TC_CAP * 32); // [2 halves][256 rows]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(thr_sh + 2 * TC_BM);
+    uint8_t* q_mem = Ys + TC_NST * unit;                  // [TC_CONS_WARPS][Q_CAP][Q_ENTRY]
+    float2* lists = reinterpret_cast<float2*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][LIST_STRIDE] (key, idx)
+    float* thr_hi_s = reinterpret_cast<float*>(lists + TC_BM * LIST_STRIDE);           // [256] bound read by the scanners
+    float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
+    float* thr_mass_s = thr_list_s + TC_BM;
+    float* kr_s = thr_mass_s + TC_BM;
+    float* r_s = kr_s + TC_BM;
+    float* l_s = r_s + TC_BM;
+    float* xx_s = l_s + TC_BM;                            // [256] |x~|^2
+    float* worst_s = xx_s + TC_BM;                        // [256] largest key of the row's list (slot number in its low bits)
+    QCtl* qctl = reinterpret_cast<QCtl*>(worst_s + TC_BM);   // [TC_CONS_WARPS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qctl + TC_CONS_WARPS);
     uint64_t* full = bars;                 // [NST]
     uint64_t* empty = bars + TC_NST;       // [NST]
     uint64_t* tfull = bars + 2 * TC_NST;   // [2]
@@ -399,11 +363,37 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < TC_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, TC_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, TC_SCAN_WARPS); }
         mbar_init(xfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmXe);
         tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmYe);
+        for (int c = 0; c < TC_CONS_WARPS; ++c) qctl[c] = QCtl{0u, 0u, 0u, 0u};
+    }
+    // row state, lists and queue sequence words (all threads)
+    for (int e = threadIdx.x; e < TC_CONS_WARPS * Q_CAP; e += TC_THREADS) *reinterpret_cast<unsigned*>(q_mem + e * Q_ENTRY + 72) = 0u;
+    for (int e = threadIdx.x; e < TC_BM * LIST_STRIDE; e += TC_THREADS)      // empty slots: LIST_EMPTY with the slot number in the low bits
+        lists[e] = make_float2(__uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)((e % LIST_STRIDE) & 15)), __int_as_float(-1));
+    for (int rl = threadIdx.x; rl < TC_BM; rl += TC_THREADS) {
+        const int row = row0 + rl;
+        float thl = -INFINITY, thm = -INFINITY, kr = INFINITY, r = INFINITY, xx = 0.f;   // padding rows never enqueue
+        if (row < p.N) {
+            xx = __ldg(p.xx + (size_t)b * p.N + row);
+            thl = kPrime ? INFINITY : 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row)) - xx);
+            if (kSoft) {
+                // softmax reference from the priming pass (sample minimum >= row minimum: the window it gives is a superset)
+                const float d2s = __uint_as_float(__ldcg(p.rmin_global + (size_t)b * p.N + row));
+                thm = INFINITY;
+                if (d2s < INFINITY) {
+                    kr = 0.5f * (d2s - xx); r = sqrtf(fmaxf(d2s, 0.f));
+                    const float te = r + p.cut_over_alpha;
+                    thm = 0.5f * (te * te - xx);
+                }
+            }
+        }
+        thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = 0.f; xx_s[rl] = xx;
+        worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
+        thr_hi_s[rl] = kSoft ? fmaxf(thl, thm) : thl;
     }
     if (warp == 1) {                        // TMEM: all 512 columns (2 accumulator stages x 2 sub-blocks x 128)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
@@ -443,7 +433,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const uint32_t ph = (it / TC_NST) & 1;
                 const int acc = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(tempty + acc, aph ^ 1);          // epilogue has drained this accumulator stage
+                mbar_wait(tempty + acc, aph ^ 1);          // scanners have drained this accumulator stage
                 mbar_wait(full + s, ph);                   // Y tile landed
                 tc_fence_after();
                 const uint32_t ya0 = smem_u32(Ys + s * unit);
@@ -460,86 +450,185 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     tc_mma_f16(d_tmem, umma_desc_sw32(xa0 + p.KB * TC_BLK_BYTES), umma_desc_sw32(ya0 + p.KB * TC_BLK_BYTES), p.idesc, 1u);
                 }
                 tc_commit(empty + s);                      // smem slot reusable once these MMAs retire
-                tc_commit(tfull + acc);                    // accumulators ready for the epilogue
+                tc_commit(tfull + acc);                    // accumulators ready for the scanners
             }
         }
-    } else {
-        // =============================== epilogue ===============================
+    } else if (warp < 2 + TC_SCAN_WARPS) {
+        // =============================== scanners ===============================
         const int ew = warp - 2;                           // 0..15
         const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's
         const int grp = ew >> 2;                           // 0..3
         const int sb = grp >> 1;                           // row sub-block
         const int half = grp & 1;                          // columns half*64 .. +63 of each tile
-        const int rloc = sb * TC_SUB + quarter * 32 + lane;    // row inside the CTA block
-        const int row = row0 + rloc;
-        const bool row_ok = row < p.N;
-        const float xx = row_ok ? __ldg(p.xx + (size_t)b * p.N + row) : 0.f;
-        const uint32_t buf_a = smem_u32(cand_buf) + (uint32_t)(ew * TC_CAP * 32 + lane) * 8u;
-        const uint32_t thr_mine_a = smem_u32(thr_sh) + (uint32_t)(half * TC_BM + rloc) * 4u;
-        const uint32_t thr_other_a = smem_u32(thr_sh) + (uint32_t)((1 - half) * TC_BM + rloc) * 4u;
-        unsigned* thr_g = p.thr_global + (size_t)b * p.N + (row_ok ? row : 0);     // true-domain d^2 bits
-        sts_f32(thr_mine_a, INFINITY);
-        EpiState<K> st;
-        st.list.init();
-        st.thr_list = -INFINITY;                           // padding rows never hit
-        if (row_ok) st.thr_list = kPrime ? INFINITY : 0.5f * (__uint_as_float(__ldcg(thr_g)) - xx);
-        st.thr_mass = -INFINITY;                           // no window terms until the running minimum exists
-        st.thr_hi = st.thr_list;
-        st.kr = INFINITY; st.r = INFINITY; st.l = 0.f; st.wr = buf_a;
+        const int cq = sb * 4 + quarter;                    // consumer / queue of this warp's rows
+        const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(sb * TC_SUB + quarter * 32 + lane) * 4u;
+        const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cq * Q_CAP * Q_ENTRY;
+        const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * TC_BN + half * 64;
 #pragma unroll 1
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int col0 = (tile0 + it * p.tile_stride) * TC_BN + half * 64;
-            // thresholds published by the row's other lists: the global one (other column splits) is fetched before
-            // the wait for the accumulator and consumed after it, so its latency hides behind the MMA
-            unsigned tg_bits = 0x7f800000u;
-            if (!kPrime && p.multi_split && row_ok && (it & 3) == 0) tg_bits = __ldcg(thr_g);
             mbar_wait_backoff(tfull + acc, aph);
             tc_fence_after();
-            if (!kPrime && row_ok) {
-                const float t = fminf(lds_f32(thr_other_a), 0.5f * (__uint_as_float(tg_bits) - xx));
-                if (t < st.thr_list) { st.thr_list = t; st.thr_hi = kSoft ? fmaxf(t, st.thr_mass) : t; }
-            }
             const uint32_t taddr = t_lane + acc * 2 * TC_BN;
             // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
             float ka[TC_CHUNK], kb[TC_CHUNK];
             tc_ld16_issue(taddr, ka);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + TC_CHUNK, kb);
-            process_chunk<kSoft, kPrime>(st, ka, col0, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
+            scan_chunk(ka, col0, thr_hi_a, q_a, ctl_a, lane, lane);
             tc_ld16_wait(kb);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
-            process_chunk<kSoft, kPrime>(st, kb, col0 + TC_CHUNK, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
+            scan_chunk(kb, col0 + TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
-            process_chunk<kSoft, kPrime>(st, ka, col0 + 2 * TC_CHUNK, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
+            scan_chunk(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane);
             tc_ld16_wait(kb);
             tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
-            process_chunk<kSoft, kPrime>(st, kb, col0 + 3 * TC_CHUNK, buf_a, thr_mine_a, thr_other_a, thr_g, row_ok, xx, p);
+            scan_chunk(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane);
         }
-        epi_flush<kSoft>(st, buf_a, xx, p.a2);
-        if (row_ok) {
-            if (kPrime) {
-                const float w = st.list.worst();
-                if (w != INFINITY) atomicMin(thr_g, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
-            } else {
-                const size_t g_row = (size_t)b * p.N + row;
-                const int pidx = split * 2 + half;
-                const size_t base = (g_row * p.cb.P + pidx) * KC;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(reinterpret_cast<unsigned*>(__cvta_shared_to_generic(ctl_a + 8)), 1u);      // QCtl::done
+        }
+    } else {
+        // =============================== consumers ===============================
+        // Row lists are UNSORTED K-slot sets in shared memory; every stored key carries its slot number in its 4 low
+        // mantissa bits, so "the worst entry and where it sits" is one max-tree.  Entry keys get their column offset
+        // packed the same way, so "the best not yet handled key and its column" is one min-tree.  (16 ulp of
+        // perturbation, covered by the certificate's E2 term; exact distances are recomputed by finalize anyway.)
+        const int cw = warp - (2 + TC_SCAN_WARPS);          // consumer index: (sub-block, quarter)
+        const int rl0 = cw * 32;                             // first CTA-local row served (sub-block * 128 + quarter * 32)
+        const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cw * Q_CAP * Q_ENTRY;
+        const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cw * sizeof(QCtl);
+        unsigned head = 0;
+        for (;;) {
+            const unsigned g = head + (unsigned)lane;
+            const uint32_t ea = q_a + (g % Q_CAP) * Q_ENTRY;
+            const bool ready = lds_u32_acquire(ea + 72) == g / Q_CAP + 1u;
+            const unsigned rb = __ballot_sync(kFull, ready);
+            const int n = (rb == kFull) ? 32 : __ffs(~rb) - 1;        // leading ready entries (queue order)
+            if (n == 0) {
+                if (lds_u32_acquire(ctl_a + 8) == 2u && lds_u32_volatile(ctl_a) == head) break;   // 2 scanner warps (column halves) feed a queue
+                __nanosleep(32);
+                continue;
+            }
+            const bool active = lane < n;
+            float k[TC_CHUNK];
+            int rl = -1 - lane, cbase = 0;                            // inactive lanes: unique pseudo rows
+            if (active) {
+                const float4 k0 = lds_v4(ea), k1 = lds_v4(ea + 16), k2 = lds_v4(ea + 32), k3 = lds_v4(ea + 48);
+                k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
+                k[8] = k2.x; k[9] = k2.y; k[10] = k2.z; k[11] = k2.w; k[12] = k3.x; k[13] = k3.y; k[14] = k3.z; k[15] = k3.w;
+                const float2 rc = lds_v2(ea + 64);
+                rl = rl0 + __float_as_int(rc.x); cbase = __float_as_int(rc.y);
 #pragma unroll
-                for (int t = 0; t < K; ++t) {
-                    const float k = st.list.key[t];
-                    p.cb.key[base + t] = k == INFINITY ? INFINITY : fmaxf(fmaf(2.f, k, xx), 0.f);    // back to the true d^2 domain
-                    p.cb.idx[base + t] = st.list.idx[t];
+                for (int t = 0; t < TC_CHUNK; ++t) k[t] = __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t);
+            } else {
+#pragma unroll
+                for (int t = 0; t < TC_CHUNK; ++t) k[t] = INFINITY;
+            }
+            // entries of the same row are processed one after the other, in queue order
+            const unsigned peers = __match_any_sync(kFull, rl);
+            bool todo = active;
+            unsigned done_mask = ~__ballot_sync(kFull, active);       // inactive lanes count as done
+            while (done_mask != kFull) {
+                const bool mine = todo && (__ffs(peers & ~done_mask) - 1 == lane);
+                // row state of the lanes whose turn it is
+                float xx = 0.f, thl = -INFINITY, thm = -INFINITY, kr = 0.f, r = 0.f, l = 0.f, worst = -INFINITY;
+                float2* L = lists + (mine ? rl : 0) * LIST_STRIDE;
+                if (mine) {
+                    xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; r = r_s[rl]; l = l_s[rl];
+                    worst = worst_s[rl];
+                    if (!kPrime && p.multi_split)
+                        thl = fminf(thl, 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row0 + rl)) - xx));
                 }
-                p.cb.l[g_row * p.cb.P + pidx] = st.l;
-                p.cb.r[g_row * p.cb.P + pidx] = st.r;
-                // discard bound of this partial list (true domain): everything it dropped has a key >= thr_list
-                p.cb.t[g_row * p.cb.P + pidx] = st.thr_list == INFINITY ? INFINITY : fmaxf(fmaf(2.f, st.thr_list, xx), 0.f);
+                bool changed = false;
+                float prev = -INFINITY;                               // packed keys handled so far are <= prev
+                // warp-uniform loop: every trip handles the next-best key of every lane that still has one below its bound
+                for (;;) {
+                    float m;
+                    if (prev == -INFINITY) {                          // first trip of a lane: plain minimum
+                        m = min16(k);
+                    } else {
+                        float cand[TC_CHUNK];
+#pragma unroll
+                        for (int t = 0; t < TC_CHUNK; ++t) cand[t] = k[t] > prev ? k[t] : INFINITY;
+                        m = min16(cand);
+                    }
+                    if (kSoft && mine && m < kr) {                    // new row minimum: move the reference of the mass
+                        const float rn = key_dist_approx(m, xx);
+                        if (l != 0.f) l *= ex2_approx(-p.a2 * (r - rn));
+                        kr = m; r = rn;
+                        const float te = rn + p.cut_over_alpha;
+                        thm = 0.5f * (te * te - xx);
+                    }
+                    const float lim = fminf(thl, worst);
+                    const bool go = mine && m < (kSoft ? fmaxf(lim, thm) : lim);
+                    if (!__any_sync(kFull, go)) break;
+                    if (go) {
+                        prev = m;
+                        float out = m;
+                        if (m < lim) {                                // list candidate: replace the worst entry, find the new worst
+                            out = worst;
+                            const int ws = (int)(__float_as_uint(worst) & 15u);
+                            L[ws] = make_float2(__uint_as_float((__float_as_uint(m) & ~15u) | (unsigned)ws),
+                                                __int_as_float(cbase + (int)(__float_as_uint(m) & 15u)));
+                            float w = -INFINITY;
+#pragma unroll
+                            for (int t = 0; t < K; ++t) w = fmaxf(w, L[t].x);
+                            worst = w;
+                            changed = true;
+                        }
+                        if (kSoft && out < thm) l += ex2_approx(-p.a2 * (key_dist_approx(out, xx) - r));
+                    }
+                }
+                if (mine) {
+                    thl = fminf(thl, worst);
+                    thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = l; worst_s[rl] = worst;
+                    *reinterpret_cast<volatile float*>(thr_hi_s + rl) = kSoft ? fmaxf(thl, thm) : thl;
+                    if (!kPrime && p.multi_split && changed && worst < LIST_EMPTY)
+                        atomicMin(p.thr_global + (size_t)b * p.N + row0 + rl, __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
+                    todo = false;
+                }
+                done_mask = __ballot_sync(kFull, !todo);
+            }
+            head += (unsigned)n;
+            __syncwarp();
+            if (lane == 0) sts_u32_release(ctl_a + 4, head);          // QCtl::head: frees the slots
+        }
+        // ---- results of the 32 rows of this consumer
+        {
+            const int rl = rl0 + lane;
+            const int row = row0 + rl;
+            if (row < p.N) {
+                const float xx = xx_s[rl];
+                const float2* L = lists + rl * LIST_STRIDE;
+                if (kPrime) {
+                    float w = -INFINITY, m = INFINITY;
+                    for (int t = 0; t < K; ++t) { w = fmaxf(w, L[t].x); m = fminf(m, L[t].x); }
+                    if (w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
+                    if (m < LIST_EMPTY) atomicMin(p.rmin_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, m, xx), 0.f)));
+                } else {
+                    const size_t g_row = (size_t)b * p.N + row;
+                    const size_t base = (g_row * p.cb.P + split) * KC;
+                    for (int t = 0; t < K; ++t) {
+                        const float2 e = L[t];
+                        const bool has = e.x < LIST_EMPTY;
+                        p.cb.key[base + t] = has ? fmaxf(fmaf(2.f, e.x, xx), 0.f) : INFINITY;      // back to the true d^2 domain
+                        p.cb.idx[base + t] = has ? __float_as_int(e.y) : -1;
+                    }
+                    const float thl = thr_list_s[rl];
+                    p.cb.l[g_row * p.cb.P + split] = l_s[rl];
+                    p.cb.r[g_row * p.cb.P + split] = r_s[rl];
+                    // discard bound of this list (true domain): everything it dropped has a key >= thr_list
+                    p.cb.t[g_row * p.cb.P + split] = thl >= LIST_EMPTY ? INFINITY : fmaxf(fmaf(2.f, thl, xx), 0.f);
+                }
             }
         }
     }
@@ -608,10 +697,10 @@ static int choose_split(int B, int N, int M) {
     return best;
 }
 
-int tc_num_partials(int B, int N, int M) { return 2 * choose_split(B, N, M); }
+int tc_num_partials(int B, int N, int M) { return choose_split(B, N, M); }
 
 struct TcWs {
-    uint16_t* Xh; uint16_t* Yh; float* xx; float* yy_max; unsigned* thr_g;
+    uint16_t* Xh; uint16_t* Yh; float* xx; float* yy_max; unsigned* thr_g; unsigned* rmin_g;
     int Cpad, Ktot, Mpad;
 };
 
@@ -625,7 +714,8 @@ static size_t tc_ws_layout(void* base, size_t cap, int B, int N, int M, int C, T
     w.Yh = ws.take<uint16_t>((size_t)B * w.Mpad * w.Ktot);
     w.xx = ws.take<float>((size_t)B * N);
     w.yy_max = ws.take<float>((size_t)B);
-    w.thr_g = ws.take<unsigned>((size_t)B * N);
+    w.thr_g = ws.take<unsigned>((size_t)2 * B * N);      // thr_g | rmin_g, filled with +inf by one launch
+    w.rmin_g = w.thr_g + (size_t)B * N;
     if (out) *out = w;
     return align_up(ws.off, 256);
 }
@@ -670,7 +760,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     TcParams p{};
     p.N = N; p.M = M; p.KB = w.Cpad / TC_KBLK;
     p.tiles_total = ceil_div(M, TC_BN);
-    const int S = cb.P / 2;
+    const int S = cb.P;
     p.tiles_per_split = ceil_div(p.tiles_total, S);
     p.a2 = alpha * kLog2e;
     // softmax window of the 16-bit pass: terms below exp(-cut) of the row maximum are dropped; the dropped mass is
@@ -683,13 +773,15 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_SUB >> 4) << 24);
     p.xx = w.xx; p.cb = cb;
     p.thr_global = w.thr_g;
+    p.rmin_global = w.rmin_g;
     p.multi_split = S > 1;
     p.tile_stride = 1;
-    fill_u32_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(w.thr_g, 0x7f800000u, B * N);    // +inf (memset cannot write it)
+    fill_u32_kernel<<<ceil_div(2 * B * N, 256), 256, 0, st>>>(w.thr_g, 0x7f800000u, 2 * B * N);    // +inf (memset cannot write it)
     DVM_LAUNCH_CHECK();
 
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
-    const size_t smem = (2 + TC_NST) * unit + (size_t)TC_EPI_WARPS * TC_CAP * 32 * 8 + 2 * TC_BM * sizeof(float) + 128;
+    const size_t smem = (2 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 8 * TC_BM * sizeof(float)
+                        + TC_CONS_WARPS * sizeof(QCtl) + 128;
     auto kern = soft ? softmap_cand_tc_kernel<true, false> : softmap_cand_tc_kernel<false, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
     static bool attr_done = false;
