@@ -102,6 +102,23 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// lean form for the issue loop: descriptors as (lo, hi) halves -- hi is a per-layout constant, lo = a precomputed base
+// plus a small immediate -- so one MMA costs two integer adds and the instruction itself
+template <bool kAccumulate>
+__device__ __forceinline__ void tc_mma_f16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc) {
+    if (kAccumulate)
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t* u = reinterpret_cast<uint32_t*>(v);
     asm volatile(
@@ -426,7 +443,18 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
+        // A single thread issues 18 MMAs per tile; its instruction stream is on the critical path (it was ~20
+        // instructions per MMA with the descriptors rebuilt every time: 2200 clk per tile, the ceiling of the whole
+        // kernel).  Descriptor halves are precomputed; the loop body is two adds + the MMA.
         if (lane == 0) {
+            constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
+            constexpr uint32_t HI32 = (256u >> 4) | (1u << 14) | (6u << 29);       // SBO 256 B, version 1, SWIZZLE_32B
+            const uint32_t xlo0 = ((smem_u32(Xs) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t xlo1 = ((smem_u32(Xs + unit) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t ylo_s0 = ((smem_u32(Ys) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t ystep = (uint32_t)unit >> 4;                            // stage stride in descriptor units
+            const uint32_t ext = (uint32_t)(p.KB * TC_BLK_BYTES) >> 4;
+            const uint32_t idesc = p.idesc;
             mbar_wait(xfull, 0);
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_NST;
@@ -436,19 +464,26 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 mbar_wait(tempty + acc, aph ^ 1);          // scanners have drained this accumulator stage
                 mbar_wait(full + s, ph);                   // Y tile landed
                 tc_fence_after();
-                const uint32_t ya0 = smem_u32(Ys + s * unit);
+                const uint32_t ylo = ylo_s0 + (uint32_t)s * ystep;
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 2) * TC_BN, d1 = d0 + TC_BN;
+                // first K block: k = 0 overwrites the accumulators
+                tc_mma_f16_lohi<false>(d0, xlo0, ylo, HI128, idesc);
+                tc_mma_f16_lohi<false>(d1, xlo1, ylo, HI128, idesc);
 #pragma unroll
-                for (int sb = 0; sb < 2; ++sb) {
-                    const uint32_t d_tmem = tmem_base + (acc * 2 + sb) * TC_BN;
-                    const uint32_t xa0 = smem_u32(Xs + sb * unit);
-                    for (int kb = 0; kb < p.KB; ++kb) {
-                        const uint32_t xa = xa0 + kb * TC_BLK_BYTES, ya = ya0 + kb * TC_BLK_BYTES;
-#pragma unroll
-                        for (int k = 0; k < TC_KBLK / 16; ++k)     // UMMA_K = 16 -> +32 bytes inside the swizzle row
-                            tc_mma_f16(d_tmem, umma_desc_sw128(xa + k * 32), umma_desc_sw128(ya + k * 32), p.idesc, (kb | k) != 0);
-                    }
-                    tc_mma_f16(d_tmem, umma_desc_sw32(xa0 + p.KB * TC_BLK_BYTES), umma_desc_sw32(ya0 + p.KB * TC_BLK_BYTES), p.idesc, 1u);
+                for (int k = 1; k < TC_KBLK / 16; ++k) {   // UMMA_K = 16 -> +32 bytes = +2 descriptor units inside the swizzle row
+                    tc_mma_f16_lohi<true>(d0, xlo0 + 2 * k, ylo + 2 * k, HI128, idesc);
+                    tc_mma_f16_lohi<true>(d1, xlo1 + 2 * k, ylo + 2 * k, HI128, idesc);
                 }
+                if (p.KB == 2) {
+                    constexpr uint32_t kb1 = TC_BLK_BYTES >> 4;
+#pragma unroll
+                    for (int k = 0; k < TC_KBLK / 16; ++k) {
+                        tc_mma_f16_lohi<true>(d0, xlo0 + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
+                        tc_mma_f16_lohi<true>(d1, xlo1 + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
+                    }
+                }
+                tc_mma_f16_lohi<true>(d0, xlo0 + ext, ylo + ext, HI32, idesc);         // norm block
+                tc_mma_f16_lohi<true>(d1, xlo1 + ext, ylo + ext, HI32, idesc);
                 tc_commit(empty + s);                      // smem slot reusable once these MMAs retire
                 tc_commit(tfull + acc);                    // accumulators ready for the scanners
             }
