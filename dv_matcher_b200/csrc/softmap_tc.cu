@@ -23,23 +23,22 @@
 
 namespace dvm {
 
-constexpr int TC_SUB = 128;           // rows per CTA (its half of the UMMA M = 256 of the CTA pair)
-constexpr int TC_BM = 2 * TC_SUB;     // rows per CTA PAIR (cluster of 2, tcgen05 cta_group::2)
-constexpr int TC_BN = 256;            // columns per tile (UMMA N); each CTA of the pair stages 128 of them
+constexpr int TC_SUB = 128;           // rows per UMMA (M)
+constexpr int TC_BM = 2 * TC_SUB;     // rows per CTA
+constexpr int TC_BN = 128;            // columns per tile (UMMA N)
 constexpr int TC_KBLK = 64;           // 16-bit elements per 128-byte swizzle row
 constexpr int TC_KEXT = 16;           // extra K block: norm columns (one UMMA K step), 32-byte swizzle rows
 constexpr int TC_SCAN_WARPS = 16;      // epilogue scanners
-constexpr int TC_CONS_WARPS = 4;       // epilogue consumers (one per 32 rows = TMEM lane quarter)
+constexpr int TC_CONS_WARPS = 8;       // epilogue consumers (one per 32 rows: sub-block x TMEM lane quarter)
 constexpr int TC_THREADS = 64 + 32 * (TC_SCAN_WARPS + TC_CONS_WARPS);
-constexpr int TC_NST = 3;             // Y ring depth
+constexpr int TC_NST = 2;             // Y ring depth
 constexpr int TC_BLK_BYTES = 128 * 128;        // one 128-row x 64-element K block
 constexpr int TC_EXT_BYTES = 128 * 32;         // one 128-row x 16-element K block
 constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_CHUNK = 16;               // columns per min-tree
 constexpr unsigned kFull = 0xffffffffu;
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's leader CTA
 constexpr int TC_PRIME_STRIDE = 16;        // priming pass: every 16th tile
-constexpr int TC_PRIME_MIN_TILES = 64;      // ... when the sweep has at least this many tiles (M >= 16k)
+constexpr int TC_PRIME_MIN_TILES = 128;     // ... when the sweep has at least this many tiles (M >= 16k)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers (forms cross-checked against CUTLASS's cute/arch/*sm100* and cutlass/arch/barrier.h)
@@ -87,24 +86,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// pair (cta_group::2) forms: the TMA of either CTA lands in its OWN shared memory but signals the LEADER's barrier
-__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {        // arrive on the leader CTA's copy of `bar`
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {            // arrives on `bar` in BOTH CTAs once the MMAs retire
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -129,13 +110,13 @@ __device__ __forceinline__ void tc_mma_f16_lohi(uint32_t tmem_d, uint32_t alo, u
         asm volatile(
             "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
             "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
             ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
     else
         asm volatile(
             "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
             "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
             ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
@@ -360,39 +341,38 @@ __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase
 
 // kPrime: priming pass -- strided tile sample, K = KP, hard mode, only outputs are thr_global / rmin_global.
 template <bool kSoft, bool kPrime>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXe,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYe, const TcParams p) {
     constexpr int K = kPrime ? KP : KC;
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzled operand tiles need 1024-byte alignment (checked below)
     const int unit = p.KB * TC_BLK_BYTES + TC_EXT_BYTES;  // one 128-row operand block, all of K
-    uint8_t* Xs = smem;                                   // [KB x 16 KB | 4 KB]: this CTA's 128 rows (its half of UMMA M = 256)
-    uint8_t* Ys = Xs + unit;                              // [NST][KB x 16 KB | 4 KB]: this CTA's 128 columns of every tile (half of N)
+    uint8_t* Xs = smem;                                   // [2 sub-blocks][KB x 16 KB | 4 KB]
+    uint8_t* Ys = Xs + 2 * unit;                          // [NST][KB x 16 KB | 4 KB]
     uint8_t* q_mem = Ys + TC_NST * unit;                  // [TC_CONS_WARPS][Q_CAP][Q_ENTRY]
-    float2* lists = reinterpret_cast<float2*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [128][LIST_STRIDE] (key, idx)
-    float* thr_hi_s = reinterpret_cast<float*>(lists + TC_SUB * LIST_STRIDE);          // [128] bound read by the scanners
-    float* thr_list_s = thr_hi_s + TC_SUB;                // [128] consumer-private row state from here on
-    float* thr_mass_s = thr_list_s + TC_SUB;
-    float* kr_s = thr_mass_s + TC_SUB;
-    float* r_s = kr_s + TC_SUB;
-    float* l_s = r_s + TC_SUB;
-    float* xx_s = l_s + TC_SUB;                           // [128] |x~|^2
-    float* worst_s = xx_s + TC_SUB;                       // [128] largest key of the row's list (slot number in its low bits)
-    QCtl* qctl = reinterpret_cast<QCtl*>(worst_s + TC_SUB);  // [TC_CONS_WARPS]
+    float2* lists = reinterpret_cast<float2*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][LIST_STRIDE] (key, idx)
+    float* thr_hi_s = reinterpret_cast<float*>(lists + TC_BM * LIST_STRIDE);           // [256] bound read by the scanners
+    float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
+    float* thr_mass_s = thr_list_s + TC_BM;
+    float* kr_s = thr_mass_s + TC_BM;
+    float* r_s = kr_s + TC_BM;
+    float* l_s = r_s + TC_BM;
+    float* xx_s = l_s + TC_BM;                            // [256] |x~|^2
+    float* worst_s = xx_s + TC_BM;                        // [256] largest key of the row's list (slot number in its low bits)
+    QCtl* qctl = reinterpret_cast<QCtl*>(worst_s + TC_BM);   // [TC_CONS_WARPS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(qctl + TC_CONS_WARPS);
-    uint64_t* full = bars;                 // [NST]   leader's copy is used: expect_tx covers the TMA of BOTH CTAs
-    uint64_t* empty = bars + TC_NST;       // [NST]   per CTA, signalled by the leader's multicast commit
-    uint64_t* tfull = bars + 2 * TC_NST;   // [2]     per CTA, multicast commit
-    uint64_t* tempty = tfull + 2;          // [2]     leader's copy: 2 x 16 scanner warps arrive
-    uint64_t* xfull = tempty + 2;          // [1]     leader's copy
+    uint64_t* full = bars;                 // [NST]
+    uint64_t* empty = bars + TC_NST;       // [NST]
+    uint64_t* tfull = bars + 2 * TC_NST;   // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint64_t* xfull = tempty + 2;          // [1]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfull + 1);
 
     const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction: lives in uniform registers
     const int lane = threadIdx.x & 31;
-    const uint32_t crank = cluster_ctarank();             // 0 = leader (issues the MMAs), 1 = peer
     const int b = blockIdx.z;
     const int split = blockIdx.y;
-    const int row0 = (blockIdx.x >> 1) * TC_BM + (int)crank * TC_SUB;   // first row of THIS CTA
+    const int row0 = blockIdx.x * TC_BM;
     const int tile0 = split * p.tiles_per_split;
     const int span = min(p.tiles_per_split, p.tiles_total - tile0);
     const int ntiles = (span + p.tile_stride - 1) / p.tile_stride;     // tiles tile0 + it * tile_stride
@@ -400,7 +380,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < TC_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 2 * TC_SCAN_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, TC_SCAN_WARPS); }
         mbar_init(xfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmXe);
@@ -409,9 +389,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
     // row state, lists and queue sequence words (all threads)
     for (int e = threadIdx.x; e < TC_CONS_WARPS * Q_CAP; e += TC_THREADS) *reinterpret_cast<unsigned*>(q_mem + e * Q_ENTRY + 72) = 0u;
-    for (int e = threadIdx.x; e < TC_SUB * LIST_STRIDE; e += TC_THREADS)      // empty slots: LIST_EMPTY with the slot number in the low bits
+    for (int e = threadIdx.x; e < TC_BM * LIST_STRIDE; e += TC_THREADS)      // empty slots: LIST_EMPTY with the slot number in the low bits
         lists[e] = make_float2(__uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)((e % LIST_STRIDE) & 15)), __int_as_float(-1));
-    for (int rl = threadIdx.x; rl < TC_SUB; rl += TC_THREADS) {
+    for (int rl = threadIdx.x; rl < TC_BM; rl += TC_THREADS) {
         const int row = row0 + rl;
         float thl = -INFINITY, thm = -INFINITY, kr = INFINITY, r = INFINITY, xx = 0.f;   // padding rows never enqueue
         if (row < p.N) {
@@ -432,42 +412,45 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
         thr_hi_s[rl] = kSoft ? fmaxf(thl, thm) : thl;
     }
-    if (warp == 1) {                        // TMEM of the pair: 512 columns per CTA (2 accumulator stages x 256), same warp in both CTAs
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    if (warp == 1) {                        // TMEM: all 512 columns (2 accumulator stages x 2 sub-blocks x 128)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                     // both CTAs' barriers are initialised before anybody signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        // =============================== TMA producer (both CTAs) ===============================
+        // =============================== TMA producer ===============================
         if (lane == 0) {
-            if (crank == 0) mbar_arrive_expect_tx(xfull, 2 * unit);                  // the pair's X rows: 2 x 128
-            for (int kb = 0; kb < p.KB; ++kb) tma_load_3d_pair(&tmX, xfull, Xs + kb * TC_BLK_BYTES, kb * TC_KBLK, row0, b);
-            tma_load_3d_pair(&tmXe, xfull, Xs + p.KB * TC_BLK_BYTES, 0, row0, b);
+            mbar_arrive_expect_tx(xfull, 2 * unit);
+            for (int sb = 0; sb < 2; ++sb) {
+                uint8_t* dst = Xs + sb * unit;
+                for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(&tmX, xfull, dst + kb * TC_BLK_BYTES, kb * TC_KBLK, row0 + sb * TC_SUB, b);
+                tma_load_3d(&tmXe, xfull, dst + p.KB * TC_BLK_BYTES, 0, row0 + sb * TC_SUB, b);
+            }
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_NST;
                 const uint32_t ph = (it / TC_NST) & 1;
-                mbar_wait(empty + s, ph ^ 1);                                       // own copy: the leader's commit reaches both CTAs
-                if (crank == 0) mbar_arrive_expect_tx(full + s, 2 * unit);          // both halves of the tile
+                mbar_wait(empty + s, ph ^ 1);
+                mbar_arrive_expect_tx(full + s, unit);
                 uint8_t* dst = Ys + s * unit;
-                const int col0 = (tile0 + it * p.tile_stride) * TC_BN + (int)crank * 128;   // this CTA's half of the tile's columns
-                for (int kb = 0; kb < p.KB; ++kb) tma_load_3d_pair(&tmY, full + s, dst + kb * TC_BLK_BYTES, kb * TC_KBLK, col0, b);
-                tma_load_3d_pair(&tmYe, full + s, dst + p.KB * TC_BLK_BYTES, 0, col0, b);
+                const int col0 = (tile0 + it * p.tile_stride) * TC_BN;
+                for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(&tmY, full + s, dst + kb * TC_BLK_BYTES, kb * TC_KBLK, col0, b);
+                tma_load_3d(&tmYe, full + s, dst + p.KB * TC_BLK_BYTES, 0, col0, b);
             }
         }
     } else if (warp == 1) {
-        // =============================== MMA issuer (leader CTA only) ===============================
-        // One thread of the leader issues 9 tcgen05.mma.cta_group::2 per tile (M = 256 over the pair, N = 256, K = 16
-        // each): every CTA feeds its own 128 rows of A and its own 128 columns of B from shared memory, which
-        // halves the operand bytes read per flop compared with two single-CTA M = 128 chains.
-        if (crank == 0 && lane == 0) {
+        // =============================== MMA issuer ===============================
+        // A single thread issues 18 MMAs per tile; its instruction stream is on the critical path (it was ~20
+        // instructions per MMA with the descriptors rebuilt every time: 2200 clk per tile, the ceiling of the whole
+        // kernel).  Descriptor halves are precomputed; the loop body is two adds + the MMA.
+        if (lane == 0) {
             constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
             constexpr uint32_t HI32 = (256u >> 4) | (1u << 14) | (6u << 29);       // SBO 256 B, version 1, SWIZZLE_32B
-            const uint32_t xlo = ((smem_u32(Xs) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t xlo0 = ((smem_u32(Xs) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t xlo1 = ((smem_u32(Xs + unit) >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t ylo_s0 = ((smem_u32(Ys) >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t ystep = (uint32_t)unit >> 4;                            // stage stride in descriptor units
             const uint32_t ext = (uint32_t)(p.KB * TC_BLK_BYTES) >> 4;
@@ -478,44 +461,53 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const uint32_t ph = (it / TC_NST) & 1;
                 const int acc = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(tempty + acc, aph ^ 1);          // the scanners of BOTH CTAs have drained this accumulator stage
-                mbar_wait(full + s, ph);                   // both halves of the Y tile landed
+                mbar_wait(tempty + acc, aph ^ 1);          // scanners have drained this accumulator stage
+                mbar_wait(full + s, ph);                   // Y tile landed
                 tc_fence_after();
                 const uint32_t ylo = ylo_s0 + (uint32_t)s * ystep;
-                const uint32_t d0 = tmem_base + (uint32_t)acc * TC_BN;
-                tc_mma_f16_lohi<false>(d0, xlo, ylo, HI128, idesc);                // k = 0 overwrites the accumulator
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 2) * TC_BN, d1 = d0 + TC_BN;
+                // first K block: k = 0 overwrites the accumulators
+                tc_mma_f16_lohi<false>(d0, xlo0, ylo, HI128, idesc);
+                tc_mma_f16_lohi<false>(d1, xlo1, ylo, HI128, idesc);
 #pragma unroll
-                for (int k = 1; k < TC_KBLK / 16; ++k)     // UMMA_K = 16 -> +32 bytes = +2 descriptor units inside the swizzle row
-                    tc_mma_f16_lohi<true>(d0, xlo + 2 * k, ylo + 2 * k, HI128, idesc);
+                for (int k = 1; k < TC_KBLK / 16; ++k) {   // UMMA_K = 16 -> +32 bytes = +2 descriptor units inside the swizzle row
+                    tc_mma_f16_lohi<true>(d0, xlo0 + 2 * k, ylo + 2 * k, HI128, idesc);
+                    tc_mma_f16_lohi<true>(d1, xlo1 + 2 * k, ylo + 2 * k, HI128, idesc);
+                }
                 if (p.KB == 2) {
                     constexpr uint32_t kb1 = TC_BLK_BYTES >> 4;
 #pragma unroll
-                    for (int k = 0; k < TC_KBLK / 16; ++k)
-                        tc_mma_f16_lohi<true>(d0, xlo + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
+                    for (int k = 0; k < TC_KBLK / 16; ++k) {
+                        tc_mma_f16_lohi<true>(d0, xlo0 + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
+                        tc_mma_f16_lohi<true>(d1, xlo1 + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
+                    }
                 }
-                tc_mma_f16_lohi<true>(d0, xlo + ext, ylo + ext, HI32, idesc);      // norm block
-                tc_commit_pair(empty + s);                 // smem slot reusable (both CTAs) once these MMAs retire
-                tc_commit_pair(tfull + acc);               // accumulators ready for the scanners of both CTAs
+                tc_mma_f16_lohi<true>(d0, xlo0 + ext, ylo + ext, HI32, idesc);         // norm block
+                tc_mma_f16_lohi<true>(d1, xlo1 + ext, ylo + ext, HI32, idesc);
+                tc_commit(empty + s);                      // smem slot reusable once these MMAs retire
+                tc_commit(tfull + acc);                    // accumulators ready for the scanners
             }
         }
     } else if (warp < 2 + TC_SCAN_WARPS) {
         // =============================== scanners ===============================
         const int ew = warp - 2;                           // 0..15
         const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's
-        const int cgp = ew >> 2;                           // column group: columns cgp*64 .. +63 of each 256-column tile
-        const int cq = quarter;                            // consumer / queue of this warp's rows
-        const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(quarter * 32 + lane) * 4u;
+        const int grp = ew >> 2;                           // 0..3
+        const int sb = grp >> 1;                           // row sub-block
+        const int half = grp & 1;                          // columns half*64 .. +63 of each tile
+        const int cq = sb * 4 + quarter;                    // consumer / queue of this warp's rows
+        const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(sb * TC_SUB + quarter * 32 + lane) * 4u;
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cq * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgp * 64;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * TC_BN + half * 64;
 #pragma unroll 1
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int col0 = (tile0 + it * p.tile_stride) * TC_BN + cgp * 64;
+            const int col0 = (tile0 + it * p.tile_stride) * TC_BN + half * 64;
             mbar_wait_backoff(tfull + acc, aph);
             tc_fence_after();
-            const uint32_t taddr = t_lane + acc * TC_BN;
+            const uint32_t taddr = t_lane + acc * 2 * TC_BN;
             // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
             float ka[TC_CHUNK], kb[TC_CHUNK];
             tc_ld16_issue(taddr, ka);
@@ -531,7 +523,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_wait(kb);
             tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
-            if (lane == 0) mbar_arrive_leader(tempty + acc);
+            if (lane == 0) mbar_arrive(tempty + acc);
             scan_chunk(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane);
         }
         __syncwarp();
@@ -545,8 +537,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         // mantissa bits, so "the worst entry and where it sits" is one max-tree.  Entry keys get their column offset
         // packed the same way, so "the best not yet handled key and its column" is one min-tree.  (16 ulp of
         // perturbation, covered by the certificate's E2 term; exact distances are recomputed by finalize anyway.)
-        const int cw = warp - (2 + TC_SCAN_WARPS);          // consumer index = TMEM lane quarter
-        const int rl0 = cw * 32;                             // first CTA-local row served
+        const int cw = warp - (2 + TC_SCAN_WARPS);          // consumer index: (sub-block, quarter)
+        const int rl0 = cw * 32;                             // first CTA-local row served (sub-block * 128 + quarter * 32)
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cw * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cw * sizeof(QCtl);
         unsigned head = 0;
@@ -557,7 +549,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const unsigned rb = __ballot_sync(kFull, ready);
             const int n = (rb == kFull) ? 32 : __ffs(~rb) - 1;        // leading ready entries (queue order)
             if (n == 0) {
-                if (lds_u32_acquire(ctl_a + 8) == 4u && lds_u32_volatile(ctl_a) == head) break;   // 4 scanner warps (column groups) feed a queue
+                if (lds_u32_acquire(ctl_a + 8) == 2u && lds_u32_volatile(ctl_a) == head) break;   // 2 scanner warps (column halves) feed a queue
                 __nanosleep(32);
                 continue;
             }
@@ -678,10 +670,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                     // nobody of the pair still signals barriers / reads shared memory of the other
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -733,8 +724,8 @@ static int choose_split(int B, int N, int M) {
         if (s > 1 && tiles / s < 8) break;                       // keep >= 8 tiles per CTA to amortise the X load
         const int tps = ceil_div(tiles, s);
         if ((s - 1) * tps >= tiles) continue;                    // would leave an empty split
-        const long long ctas = (long long)row_blocks * s * B;          // CTA pairs
-        const double waves = (double)ctas / (kNumSM / 2);
+        const long long ctas = (long long)row_blocks * s * B;
+        const double waves = (double)ctas / kNumSM;
         const double eff = waves / ceil(waves) - 0.02 * (s - 1); // prefer fewer partial lists on ties
         if (eff > best_eff) { best_eff = eff; best = s; }
     }
@@ -814,7 +805,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     // instruction descriptor: D=f32 (bits 4-5 = 1), A/B format (0 = f16, 1 = bf16) at bits 7-9 / 10-12, K-major A and B,
     // N >> 3 at bits 17-22, M >> 4 at bits 24-28
     const uint32_t fmt = bf16 ? 1u : 0u;
-    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_SUB >> 4) << 24);
     p.xx = w.xx; p.cb = cb;
     p.thr_global = w.thr_g;
     p.rmin_global = w.rmin_g;
@@ -824,7 +815,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     DVM_LAUNCH_CHECK();
 
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
-    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_SUB * LIST_STRIDE * 8 + 8 * TC_SUB * sizeof(float)
+    const size_t smem = (2 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 8 * TC_BM * sizeof(float)
                         + TC_CONS_WARPS * sizeof(QCtl) + 128;
     auto kern = soft ? softmap_cand_tc_kernel<true, false> : softmap_cand_tc_kernel<false, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
@@ -840,11 +831,11 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 16th tile (6 % of the sweep's MMA work)
         TcParams pp = p;
         pp.tile_stride = TC_PRIME_STRIDE; pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
-        dim3 gridp(2 * ceil_div(N, TC_BM), 1, B);                 // clusters of 2 CTAs along x
+        dim3 gridp(ceil_div(N, TC_BM), 1, B);
         kprime<<<gridp, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, pp);
         DVM_LAUNCH_CHECK();
     }
-    dim3 grid(2 * ceil_div(N, TC_BM), S, B);
+    dim3 grid(ceil_div(N, TC_BM), S, B);
     kern<<<grid, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, p);
     prof_end(st);
     DVM_LAUNCH_CHECK();
