@@ -315,10 +315,24 @@ __device__ __forceinline__ float4 lds_v4(uint32_t a) {
     float4 r; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory"); return r;
 }
 
-// scanner: one 16-column chunk of one row
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float max16(const float (&k)[16]) {
+    return fmaxf(max3(max3(k[0], k[1], k[2]), max3(k[3], k[4], k[5]), max3(k[6], k[7], k[8])),
+                 max3(max3(k[9], k[10], k[11]), max3(k[12], k[13], k[14]), k[15]));
+}
+
+// scanner: one 16-column chunk of one row.
+// kPrivBound (hard mode): while the consumer has not published a list threshold yet (first tile of a CTA that starts
+// without a primed threshold) the thread bounds it itself -- the largest key of any chunk it has seen is >= the row's
+// 16th smallest key -- so the start-up does not flood the queue with every chunk of every row.
+template <bool kPrivBound>
 __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase, uint32_t thr_hi_a, uint32_t q_a, uint32_t ctl_a,
-                                           int row_in_q, int lane) {
-    const float th = lds_f32(thr_hi_a);
+                                           int row_in_q, int lane, float& priv, bool first_tile) {
+    float th = lds_f32(thr_hi_a);
+    if (kPrivBound) {
+        th = fminf(th, priv);
+        if (first_tile) priv = fminf(priv, max16(k));
+    }
     const bool slow = min16(k) < th;
     const unsigned mask = __ballot_sync(kFull, slow);
     if (mask == 0u) return;                                          // warp-uniform
@@ -500,6 +514,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cq * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * TC_BN + half * 64;
+        float priv = INFINITY;
 #pragma unroll 1
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
@@ -513,18 +528,18 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_issue(taddr, ka);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + TC_CHUNK, kb);
-            scan_chunk(ka, col0, thr_hi_a, q_a, ctl_a, lane, lane);
+            scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
             tc_ld16_wait(kb);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
-            scan_chunk(kb, col0 + TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane);
+            scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
-            scan_chunk(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane);
+            scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
             tc_ld16_wait(kb);
             tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
-            scan_chunk(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane);
+            scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
         }
         __syncwarp();
         if (lane == 0) {
