@@ -515,36 +515,54 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
 // =================================================================================================
 constexpr int RESC_MAX = 4096;       // flagged rows handled by the rescue scan; more -> fp32 candidate pass
 constexpr int RESC_CAP = 32;         // listed columns per row; more (mass ties) -> fp32 pass for that row
-constexpr int RESC_NCH_MAX = 256;    // column chunks
+constexpr int RESC_NCH_MAX = 2048;   // column chunks (M <= 262144 for the rescue scan; beyond: fp32 pass)
 constexpr int RESC_ROWS = 8;         // flagged rows per group
+
+constexpr int RESC_CHUNK = 128;      // columns per CTA: the Y chunk is staged ONCE in shared memory (coalesced) and reused
+                                     // for every flagged row of the batch element
 
 template <bool kSoft>
 __global__ void __launch_bounds__(256)
 rescue_scan_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M, int C,
                    const int* __restrict__ flag_list, const int* __restrict__ flag_count,
                    const float* __restrict__ flag_thr, const float* __restrict__ flag_r, float a2,
-                   int nch, int chunk, int* __restrict__ resc_cnt, int* __restrict__ resc_idx, float* __restrict__ resc_mass) {
+                   int nch, int* __restrict__ resc_cnt, int* __restrict__ resc_idx, float* __restrict__ resc_mass) {
+    extern __shared__ __align__(16) float rs_sm[];
+    const int ld = C + 4;                                    // conflict-free float4 reads, one column per lane
+    float* Ys = rs_sm;                                       // [RESC_CHUNK][ld]
+    float* xs = Ys + RESC_CHUNK * ld;                        // [RESC_ROWS][C]
     __shared__ int s_slots[RESC_MAX];
     __shared__ int s_n;
-    __shared__ __align__(16) float xs[RESC_ROWS][256];
     __shared__ float s_thr[RESC_ROWS], s_ref[RESC_ROWS];
-    __shared__ float s_part[8][RESC_ROWS];
+    __shared__ float s_part[4][RESC_ROWS];
     const int count = *flag_count;
     if (count == 0 || count > RESC_MAX) return;
     const int b = blockIdx.y, ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int c0 = ch * chunk, c1 = min(M, c0 + chunk);
+    const int c0 = ch * RESC_CHUNK;
+    const int ncol = min(RESC_CHUNK, M - c0);
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int e = tid; e < count; e += 256)
         if (flag_list[e] / N == b) s_slots[atomicAdd(&s_n, 1)] = e;
     __syncthreads();
     const int n = s_n;
-    const float* Yb = Y + (size_t)b * M * C;
+    if (n == 0) return;
+    const int c4 = C >> 2;
+    const float* Yb = Y + ((size_t)b * M + c0) * C;
+    for (int e = tid; e < ncol * c4; e += 256) {             // coalesced: consecutive threads read consecutive float4
+        const int rr = e / c4, cc = e - rr * c4;
+        *reinterpret_cast<float4*>(Ys + rr * ld + cc * 4) = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)rr * C) + cc);
+    }
+    const int col = tid & (RESC_CHUNK - 1);                  // this thread's column of the chunk
+    const int rh = tid >> 7;                                 // ... and its half of the row group (rows rh*4 .. +3)
+    const bool col_ok = col < ncol;
     for (int g0 = 0; g0 < n; g0 += RESC_ROWS) {
         __syncthreads();
-        for (int e = tid; e < RESC_ROWS * C; e += 256) {
-            const int r = e / C, c = e - r * C;
-            xs[r][c] = (g0 + r < n) ? __ldg(X + (size_t)flag_list[s_slots[g0 + r]] * C + c) : 0.f;
+        for (int e = tid; e < RESC_ROWS * c4; e += 256) {
+            const int r = e / c4, cc = e - r * c4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g0 + r < n) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)flag_list[s_slots[g0 + r]] * C) + cc);
+            *reinterpret_cast<float4*>(xs + r * C + cc * 4) = v;
         }
         if (tid < RESC_ROWS) {
             const bool ok = g0 + tid < n;
@@ -552,51 +570,45 @@ rescue_scan_kernel(const float* __restrict__ X, const float* __restrict__ Y, int
             s_ref[tid] = ok ? flag_r[s_slots[g0 + tid]] : 0.f;
         }
         __syncthreads();
-        float mass[RESC_ROWS];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* yp = Ys + col * ld;
+        const float* xp = xs + (rh * 4) * C;
+        for (int k = 0; k < C; k += 4) {
+            const float4 yv = *reinterpret_cast<const float4*>(yp + k);
 #pragma unroll
-        for (int r = 0; r < RESC_ROWS; ++r) mass[r] = 0.f;
-        for (int col = c0 + tid; col < c1; col += 256) {
-            float acc[RESC_ROWS];
-#pragma unroll
-            for (int r = 0; r < RESC_ROWS; ++r) acc[r] = 0.f;
-            const float* yp = Yb + (size_t)col * C;
-            for (int k = 0; k < C; k += 4) {
-                const float4 yv = __ldg(reinterpret_cast<const float4*>(yp + k));
-#pragma unroll
-                for (int r = 0; r < RESC_ROWS; ++r) {
-                    const float4 xv = *reinterpret_cast<const float4*>(&xs[r][k]);      // warp-broadcast
-                    float d;
-                    d = xv.x - yv.x; acc[r] = fmaf(d, d, acc[r]);
-                    d = xv.y - yv.y; acc[r] = fmaf(d, d, acc[r]);
-                    d = xv.z - yv.z; acc[r] = fmaf(d, d, acc[r]);
-                    d = xv.w - yv.w; acc[r] = fmaf(d, d, acc[r]);
-                }
+            for (int r = 0; r < 4; ++r) {
+                const float4 xv = *reinterpret_cast<const float4*>(xp + r * C + k);      // warp-broadcast
+                float d;
+                d = xv.x - yv.x; acc[r] = fmaf(d, d, acc[r]);
+                d = xv.y - yv.y; acc[r] = fmaf(d, d, acc[r]);
+                d = xv.z - yv.z; acc[r] = fmaf(d, d, acc[r]);
+                d = xv.w - yv.w; acc[r] = fmaf(d, d, acc[r]);
             }
+        }
+        float mass[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int r = 0; r < RESC_ROWS; ++r) {
-                if (g0 + r < n) {
-                    if (acc[r] <= s_thr[r]) {
-                        const int slot = s_slots[g0 + r];
-                        const int q = atomicAdd(resc_cnt + slot, 1);
-                        if (q < RESC_CAP) resc_idx[(size_t)slot * RESC_CAP + q] = col;
-                    } else if (kSoft) {
-                        mass[r] += exp2f(-a2 * (sqrtf(acc[r]) - s_ref[r]));
-                    }
+        for (int r = 0; r < 4; ++r) {
+            const int rr = rh * 4 + r;
+            if (col_ok && g0 + rr < n) {
+                if (acc[r] <= s_thr[rr]) {
+                    const int slot = s_slots[g0 + rr];
+                    const int q = atomicAdd(resc_cnt + slot, 1);
+                    if (q < RESC_CAP) resc_idx[(size_t)slot * RESC_CAP + q] = c0 + col;
+                } else if (kSoft) {
+                    mass[r] = exp2f(-a2 * (sqrtf(acc[r]) - s_ref[rr]));
                 }
             }
         }
         if (kSoft) {
+            // deterministic: lanes -> warp sum, then the 4 warps of a row half in fixed order
 #pragma unroll
-            for (int r = 0; r < RESC_ROWS; ++r) {
+            for (int r = 0; r < 4; ++r) {
                 const float v = warp_sum(mass[r]);
-                if (lane == 0) s_part[wid][r] = v;
+                if (lane == 0) s_part[wid & 3][rh * 4 + r] = v;
             }
             __syncthreads();
-            if (tid < RESC_ROWS && g0 + tid < n) {
-                float t = 0.f;
-                for (int w = 0; w < 8; ++w) t += s_part[w][tid];
-                resc_mass[(size_t)s_slots[g0 + tid] * nch + ch] = t;
-            }
+            if (tid < RESC_ROWS && g0 + tid < n)
+                resc_mass[(size_t)s_slots[g0 + tid] * nch + ch] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
         }
     }
 }
@@ -605,13 +617,14 @@ struct RescueArgs {
     const int* flag_list; const int* flag_count; const float* flag_r;
     const int* resc_cnt; const int* resc_idx; const float* resc_mass; int nch;
     int* list2; int* count2;                       // rows that still need the fp32 candidate pass
+    int active;                                    // 0: the scan did not run (M too large): hand everything to the fp32 pass
 };
 
 template <bool kSoft>
 __global__ void __launch_bounds__(FIN_WARPS * 32) rescue_finalize_kernel(FinalizeArgs a, RescueArgs r) {
     const int count = *r.flag_count;
     if (count == 0) return;
-    if (count > RESC_MAX) {                        // too many: hand every flagged row to the fp32 pass
+    if (count > RESC_MAX || !r.active) {           // too many (or no scan): hand every flagged row to the fp32 pass
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) r.list2[e] = r.flag_list[e];
         if (blockIdx.x == 0 && threadIdx.x == 0) *r.count2 = count;
         return;
@@ -677,7 +690,7 @@ static size_t softmap_ws_layout(void* base, size_t cap, int B, int N, int M, int
         rw.list2 = ws.take<int>(rows);
         rw.cnt = ws.take<int>(RESC_MAX);
         rw.idx = ws.take<int>((size_t)RESC_MAX * RESC_CAP);
-        rw.mass = ws.take<float>((size_t)RESC_MAX * RESC_NCH_MAX);
+        { int nchw = ceil_div(M, RESC_CHUNK); if (nchw > RESC_NCH_MAX) nchw = 1; rw.mass = ws.take<float>((size_t)RESC_MAX * nchw); }
         if (resc) *resc = rw;
     }
     if (simt) *simt = c1;
@@ -753,18 +766,22 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     // when it has nothing to do): threshold scan + exact emit; what even that cannot settle (> RESC_CAP columns
     // inside the threshold, or > RESC_MAX flagged rows) goes to the fp32 candidate pass.
     {
-        // column chunks of ~192 columns: a chunk of Y (96 KB at C = 128) stays in L1 while the CTA walks its flagged rows
-        int nch = ceil_div(M, 192);
-        if (nch > RESC_NCH_MAX) nch = RESC_NCH_MAX;
-        if (nch < 1) nch = 1;
-        const int chunk = ceil_div(M, nch);
-        nch = ceil_div(M, chunk);
+        const int nch = ceil_div(M, RESC_CHUNK);
         const float a2 = alpha * kLog2e;
-        dim3 grid(nch, B);
-        if (soft) rescue_scan_kernel<true><<<grid, 256, 0, st>>>(X, Y, N, M, C, flag_list, st_out, rw.flag_thr, rw.flag_r, a2, nch, chunk, rw.cnt, rw.idx, rw.mass);
-        else      rescue_scan_kernel<false><<<grid, 256, 0, st>>>(X, Y, N, M, C, flag_list, st_out, rw.flag_thr, rw.flag_r, a2, nch, chunk, rw.cnt, rw.idx, rw.mass);
-        DVM_LAUNCH_CHECK();
-        RescueArgs ra{flag_list, st_out, rw.flag_r, rw.cnt, rw.idx, rw.mass, nch, rw.list2, st_out + 2};
+        if (nch <= RESC_NCH_MAX) {
+            const size_t rsm = ((size_t)RESC_CHUNK * (C + 4) + (size_t)RESC_ROWS * C) * sizeof(float);
+            static bool attr_done = false;
+            if (!attr_done) {
+                DVM_CUDA(cudaFuncSetAttribute(rescue_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                DVM_CUDA(cudaFuncSetAttribute(rescue_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_done = true;
+            }
+            dim3 grid(nch, B);
+            if (soft) rescue_scan_kernel<true><<<grid, 256, rsm, st>>>(X, Y, N, M, C, flag_list, st_out, rw.flag_thr, rw.flag_r, a2, nch, rw.cnt, rw.idx, rw.mass);
+            else      rescue_scan_kernel<false><<<grid, 256, rsm, st>>>(X, Y, N, M, C, flag_list, st_out, rw.flag_thr, rw.flag_r, a2, nch, rw.cnt, rw.idx, rw.mass);
+            DVM_LAUNCH_CHECK();
+        }
+        RescueArgs ra{flag_list, st_out, rw.flag_r, rw.cnt, rw.idx, rw.mass, nch, rw.list2, st_out + 2, nch <= RESC_NCH_MAX ? 1 : 0};
         FinalizeArgs fr = fa;
         fr.flag_list = nullptr; fr.flag_count = nullptr; fr.flag_thr = nullptr; fr.flag_r = nullptr; fr.tie_count = nullptr;
         const int fgrid = ceil_div(RESC_MAX, FIN_WARPS);
