@@ -6,7 +6,7 @@ namespace dvm {
 
 int launch_knn3_auto(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
                      int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* ws, size_t ws_bytes, cudaStream_t st);
-size_t knn3_grid_workspace_bytes(int B, int M);
+size_t knn3_grid_workspace_bytes(int B, int N, int M);
 
 // ------------------------------------------------------------------------------------------------
 // FPS: one CTA per cloud, K dependent iterations.  Each iteration: masked min-update of the running
@@ -173,7 +173,7 @@ extern "C" size_t dvm_graph_workspace_bytes(int B, int N, int K) {
     ws.take<float>((size_t)B * K * 3);      // node coordinates
     ws.take<float>((size_t)B * N * 3);      // squared distances vertex -> 3 nodes
     ws.take<double>((size_t)B * N * 2);     // fp64 squared NN distances
-    ws.take<char>(knn3_grid_workspace_bytes(B, N));   // grid scratch of the three k-NN queries (largest: N points)
+    ws.take<char>(knn3_grid_workspace_bytes(B, N, N));   // grid scratch of the three k-NN queries (largest: N points)
     return align_up(ws.off, 256);
 }
 
@@ -191,7 +191,7 @@ extern "C" int dvm_graph_weights(const float* xyz, const int64_t* nodes_idx, int
     float* nodes_xyz = ws.take<float>((size_t)B * K * 3);
     float* d2 = ws.take<float>((size_t)B * N * 3);
     double* d2nn = ws.take<double>((size_t)B * N * 2);
-    const size_t gbytes = knn3_grid_workspace_bytes(B, N);
+    const size_t gbytes = knn3_grid_workspace_bytes(B, N, N);
     void* gws = ws.take<char>(gbytes);
     gather_nodes_kernel<<<dim3(ceil_div(K, 256), B), 256, 0, st>>>(xyz, nodes_idx, N, K, nodes_xyz);
     DVM_LAUNCH_CHECK();

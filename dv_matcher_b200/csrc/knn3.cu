@@ -120,7 +120,7 @@ static int launch_knn3_k(const float* Q, const float* R, int B, int N, int M, in
     return 0;
 }
 
-size_t knn3_grid_workspace_bytes(int B, int M);
+size_t knn3_grid_workspace_bytes(int B, int N, int M);
 int launch_knn3_grid(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
                      int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* ws, size_t ws_bytes, cudaStream_t st);
 
@@ -144,7 +144,7 @@ int launch_knn3(const float* Q, const float* R, int B, int N, int M, int k, bool
 
 int launch_knn3_auto(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
                      int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (ws && M >= KNN_GRID_MIN_M && ws_bytes >= knn3_grid_workspace_bytes(B, M))
+    if (ws && M >= KNN_GRID_MIN_M && ws_bytes >= knn3_grid_workspace_bytes(B, N, M))
         return launch_knn3_grid(Q, R, B, N, M, k, f64, idx64, idx32, d2f, d2d, ws, ws_bytes, st);
     return launch_knn3(Q, R, B, N, M, k, f64, idx64, idx32, d2f, d2d, st);
 }
@@ -188,7 +188,7 @@ using namespace dvm;
 
 extern "C" size_t dvm_knn3_workspace_bytes(int B, int N, int M) {
     if (B <= 0 || N <= 0 || M <= 0) return 0;
-    return M >= KNN_GRID_MIN_M ? knn3_grid_workspace_bytes(B, M) : 0;
+    return M >= KNN_GRID_MIN_M ? knn3_grid_workspace_bytes(B, N, M) : 0;
 }
 
 extern "C" size_t dvm_chamfer_workspace_bytes(int B, int N, int M) {

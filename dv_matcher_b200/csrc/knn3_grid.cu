@@ -214,6 +214,31 @@ grid_scatter_kernel(const float* __restrict__ R, int M, int stride, const int* _
     sorted[(size_t)b * M + pos] = make_float4(p[0], p[1], p[2], __int_as_float(i));
 }
 
+// queries sorted by the cell of the reference grid they fall into (clamped): warps then hold spatial neighbours, which walk
+// the same rows and spans (little divergence, L1-friendly).  Same count / scan / scatter machinery as the points.
+__global__ void __launch_bounds__(GRID_THREADS)
+grid_qcount_kernel(const float* __restrict__ Q, int N, const GridHeader* __restrict__ hdr, int stride,
+                   int* __restrict__ qcell, int* __restrict__ qcount) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (i >= N) return;
+    const GridHeader g = hdr[b];
+    const float* p = Q + ((size_t)b * N + i) * 3;
+    const int cx = cell_coord(p[0], g.x0, g.inv_h, g.nx), cy = cell_coord(p[1], g.y0, g.inv_h, g.ny), cz = cell_coord(p[2], g.z0, g.inv_h, g.nz);
+    const int c = (cz * g.ny + cy) * g.nx + cx;
+    qcell[(size_t)b * N + i] = c;
+    atomicAdd(qcount + (size_t)b * stride + c, 1);
+}
+
+__global__ void __launch_bounds__(GRID_THREADS)
+grid_qscatter_kernel(int N, int stride, const int* __restrict__ qcell, int* __restrict__ qcursor, int* __restrict__ qorder) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * GRID_THREADS + threadIdx.x;
+    if (i >= N) return;
+    const int pos = atomicAdd(qcursor + (size_t)b * stride + qcell[(size_t)b * N + i], 1);
+    qorder[(size_t)b * N + pos] = i;
+}
+
 // occupied x-extent of every (z, y) row of cells: rowx[row] = (first, last) non-empty cell, (1, 0) when the row is
 // empty.  ny * nz entries per cloud -- small enough to stay in L1, so that the (mostly empty) rows a far query walks
 // through are rejected without touching the cell-start array in L2.
@@ -287,7 +312,7 @@ template <typename T, int K, int GRID_LPQ, bool kSelf>
 __global__ void __launch_bounds__(GRID_THREADS)
 knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHeader* __restrict__ hdr, int stride,
                  const int* __restrict__ start, const int* __restrict__ cstart, const int2* __restrict__ rowx_all,
-                 const float4* __restrict__ sorted, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ d2f, double* __restrict__ d2d) {
+                 const float4* __restrict__ sorted, const int* __restrict__ qorder, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ d2f, double* __restrict__ d2d) {
     const int b = blockIdx.y;
     int q = blockIdx.x * (GRID_THREADS / GRID_LPQ) + threadIdx.x / GRID_LPQ;
     const int sub = threadIdx.x % GRID_LPQ;
@@ -302,6 +327,7 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
             const float4 p = __ldg(pts + q);
             qx = p.x; qy = p.y; qz = p.z; q = __float_as_int(p.w);
         } else {
+            if (qorder) q = __ldg(qorder + (size_t)b * N + q);         // cell-sorted query order
             const float* qp = Q + ((size_t)b * N + q) * 3;
             qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
         }
@@ -457,9 +483,10 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct GridWs { GridHeader* hdr; int* start; int* cursor; int* cstart; int* cell_of; float4* sorted; int* bsum; int2* rowx; int stride; int ncell_max; int nblk_max; };
+struct GridWs { GridHeader* hdr; int* start; int* cursor; int* cstart; int* cell_of; float4* sorted; int* bsum; int2* rowx;
+                int* qstart; int* qcursor; int* qcell; int* qorder; int stride; int ncell_max; int nblk_max; };
 
-static size_t grid_ws_layout(void* base, size_t cap, int B, int M, GridWs* out) {
+static size_t grid_ws_layout(void* base, size_t cap, int B, int N, int M, GridWs* out) {
     GridWs w{};
     long long nc = 4LL * M + 64;
     if (nc > (1LL << 24)) nc = 1LL << 24;
@@ -475,25 +502,29 @@ static size_t grid_ws_layout(void* base, size_t cap, int B, int M, GridWs* out) 
     w.nblk_max = ceil_div(w.ncell_max > GRID_COARSE_MAX ? w.ncell_max : GRID_COARSE_MAX, SCAN_BLOCK);
     w.bsum = ws.take<int>((size_t)2 * B * w.nblk_max);
     w.rowx = ws.take<int2>((size_t)B * w.stride);
+    w.qstart = ws.take<int>((size_t)B * w.stride);          // queries sorted by reference-grid cell (non-self queries)
+    w.qcursor = ws.take<int>((size_t)B * w.stride);
+    w.qcell = ws.take<int>((size_t)B * N);
+    w.qorder = ws.take<int>((size_t)B * N);
     if (out) *out = w;
     return align_up(ws.off, 256);
 }
 
-size_t knn3_grid_workspace_bytes(int B, int M) { return grid_ws_layout(nullptr, 0, B, M, nullptr); }
+size_t knn3_grid_workspace_bytes(int B, int N, int M) { return grid_ws_layout(nullptr, 0, B, N, M, nullptr); }
 
 template <typename T, int K, int LPQ = 1>
-static void launch_query(const float* Q, bool self, int B, int N, int M, int k, const GridWs& w,
+static void launch_query(const float* Q, bool self, const int* qorder, int B, int N, int M, int k, const GridWs& w,
                          int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, cudaStream_t st) {
     dim3 grid(ceil_div(N, GRID_THREADS / LPQ), B);
-    if (self) knn3_grid_kernel<T, K, LPQ, true><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, idx64, idx32, d2f, d2d);
-    else      knn3_grid_kernel<T, K, LPQ, false><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, idx64, idx32, d2f, d2d);
+    if (self) knn3_grid_kernel<T, K, LPQ, true><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, qorder, idx64, idx32, d2f, d2d);
+    else      knn3_grid_kernel<T, K, LPQ, false><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, qorder, idx64, idx32, d2f, d2d);
 }
 
 // k nearest neighbours of Q[B,N,3] in R[B,M,3] through a grid built on R (inside ws)
 int launch_knn3_grid(const float* Q, const float* R, int B, int N, int M, int k, bool f64,
                      int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, void* wsp, size_t ws_bytes, cudaStream_t st) {
     GridWs w;
-    const size_t need = grid_ws_layout(wsp, ws_bytes, B, M, &w);
+    const size_t need = grid_ws_layout(wsp, ws_bytes, B, N, M, &w);
     if (!wsp || need > ws_bytes) { set_error("knn3 grid: workspace too small (%zu < %zu)", ws_bytes, need); return DVM_ERR_WORKSPACE; }
     grid_setup_kernel<<<B, 1024, 0, st>>>(R, M, w.ncell_max, w.hdr);
     DVM_LAUNCH_CHECK();
@@ -514,11 +545,28 @@ int launch_knn3_grid(const float* Q, const float* R, int B, int N, int M, int k,
     grid_rowinfo_kernel<<<dim3(ceil_div(w.ncell_max, GRID_THREADS), B), GRID_THREADS, 0, st>>>(w.hdr, w.stride, w.start, w.rowx);
     DVM_LAUNCH_CHECK();
     const bool self = (Q == R) && (N == M);
+    const int* qorder = nullptr;
+    if (!self) {
+        DVM_CUDA(cudaMemsetAsync(w.qstart, 0, (size_t)B * w.stride * sizeof(int), st));
+        dim3 gq(ceil_div(N, GRID_THREADS), B);
+        grid_qcount_kernel<<<gq, GRID_THREADS, 0, st>>>(Q, N, w.hdr, w.stride, w.qcell, w.qstart);
+        DVM_LAUNCH_CHECK();
+        ScanArgs sq{w.hdr, w.stride, w.qstart, w.qcursor, GRID_COARSE_MAX + 1, w.cstart, w.bsum, w.nblk_max};
+        grid_scan_a_kernel<<<dim3(w.nblk_max, B, 1), 1024, 0, st>>>(sq, B);
+        DVM_LAUNCH_CHECK();
+        grid_scan_b_kernel<<<dim3(B, 1), 1024, 0, st>>>(sq, B);
+        DVM_LAUNCH_CHECK();
+        grid_scan_c_kernel<<<dim3(w.nblk_max, B, 1), 1024, 0, st>>>(sq, B);
+        DVM_LAUNCH_CHECK();
+        grid_qscatter_kernel<<<gq, GRID_THREADS, 0, st>>>(N, w.stride, w.qcell, w.qcursor, w.qorder);
+        DVM_LAUNCH_CHECK();
+        qorder = w.qorder;
+    }
 #define DVM_GRID_DISPATCH(T)                                                                         \
-    if (k == 1)       launch_query<T, 1, 8>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);            \
-    else if (k <= 4)  launch_query<T, 4>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);               \
-    else if (k <= 10) launch_query<T, 10>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);              \
-    else              launch_query<T, 16>(Q, self, B, N, M, k, w, idx64, idx32, d2f, d2d, st);
+    if (k == 1)       launch_query<T, 1, 8>(Q, self, qorder, B, N, M, k, w, idx64, idx32, d2f, d2d, st);            \
+    else if (k <= 4)  launch_query<T, 4>(Q, self, qorder, B, N, M, k, w, idx64, idx32, d2f, d2d, st);               \
+    else if (k <= 10) launch_query<T, 10>(Q, self, qorder, B, N, M, k, w, idx64, idx32, d2f, d2d, st);              \
+    else              launch_query<T, 16>(Q, self, qorder, B, N, M, k, w, idx64, idx32, d2f, d2d, st);
     if (f64) { DVM_GRID_DISPATCH(double) } else { DVM_GRID_DISPATCH(float) }
 #undef DVM_GRID_DISPATCH
     DVM_LAUNCH_CHECK();
