@@ -91,6 +91,121 @@ fps_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// FPS on a thread-block CLUSTER: one cluster (CS CTAs x 1024 threads) per cloud.  The points of the cloud are
+// spread over the CTAs and live in registers together with their running distance (<= FPSC_PPT per thread), so an
+// iteration is: local min-update + arg-max, block reduce, exchange of the CS block results through distributed
+// shared memory (every CTA writes its (value, index, x, y, z) into slot [parity][rank] of EVERY CTA of the
+// cluster), ONE cluster barrier, redundant final selection.  Slots are double-buffered by iteration parity, which
+// is what makes a single barrier per iteration sufficient.  Selection rule ((value desc, index asc)) and arithmetic
+// are those of fps_kernel, so the node lists stay bit-identical to the reference.
+// ------------------------------------------------------------------------------------------------
+constexpr int FPSC_PPT = 8;       // 8 x 4 registers of point state per thread (1024-thread CTAs have 64 registers)
+
+struct __align__(16) FpsSlot { float v; int i; float x, y, z; float pad[3]; };   // 32 bytes: 16-byte aligned remote stores
+
+__device__ __forceinline__ uint32_t fps_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void fps_st_remote(uint32_t addr, const FpsSlot& s) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(s.v)), "r"((unsigned)s.i),
+                 "r"(__float_as_uint(s.x)), "r"(__float_as_uint(s.y)) : "memory");
+    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr + 16), "r"(__float_as_uint(s.z)) : "memory");
+}
+__device__ __forceinline__ void fps_cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CS>
+__global__ void __launch_bounds__(FPS_THREADS)
+fps_cluster_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* __restrict__ start, int64_t* __restrict__ out) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    __shared__ FpsSlot s_slot[2][16];                        // [parity][rank]
+    const int b = blockIdx.x / CS;
+    const uint32_t rank = fps_cluster_rank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* P = xyz + (size_t)b * N * 3;
+    // point p of the cloud belongs to CTA (p / 1024) % CS, thread p % 1024, register (p / 1024) / CS
+    float px[FPSC_PPT], py[FPSC_PPT], pz[FPSC_PPT], pd[FPSC_PPT];
+#pragma unroll
+    for (int q = 0; q < FPSC_PPT; ++q) {
+        const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
+        px[q] = py[q] = pz[q] = 0.f; pd[q] = -1.f;            // padding never wins the arg-max
+        if (p < N) { px[q] = P[p * 3]; py[q] = P[p * 3 + 1]; pz[q] = P[p * 3 + 2]; pd[q] = 1e10f; }
+    }
+    int far = (int)start[b];
+    float cx = __ldg(P + far * 3), cy = __ldg(P + far * 3 + 1), cz = __ldg(P + far * 3 + 2);
+    fps_cluster_barrier();                                    // all CTAs of the cluster are running before remote stores
+    for (int it = 0; it < K; ++it) {
+        if (rank == 0 && tid == 0) out[(size_t)b * K + it] = far;
+        float bv = -1.f; int bi = 0x7fffffff; float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+        for (int q = 0; q < FPSC_PPT; ++q) {
+            const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
+            if (p < N) {
+                const float d = fps_d2(px[q], py[q], pz[q], cx, cy, cz);
+                if (d < pd[q]) pd[q] = d;
+                if (pd[q] > bv) { bv = pd[q]; bi = p; bx = px[q]; by = py[q]; bz = pz[q]; }     // ascending p per thread: strict '>' keeps the first
+            }
+        }
+        // warp arg-max (value desc, index asc), carrying the coordinates
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const float ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o), oz = __shfl_xor_sync(0xffffffffu, bz, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bx = ox; by = oy; bz = oz; }
+        }
+        if (lane == 0) { s_v[wid] = bv; s_i[wid] = bi; }
+        __shared__ float s_x[32], s_y[32], s_z[32];
+        if (lane == 0) { s_x[wid] = bx; s_y[wid] = by; s_z[wid] = bz; }
+        __syncthreads();
+        if (wid == 0) {
+            bv = s_v[lane]; bi = s_i[lane]; bx = s_x[lane]; by = s_y[lane]; bz = s_z[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const float ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o), oz = __shfl_xor_sync(0xffffffffu, bz, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bx = ox; by = oy; bz = oz; }
+            }
+            if (lane < CS) {                                   // lane r publishes this CTA's result into CTA r
+                FpsSlot s{bv, bi, bx, by, bz, {0.f, 0.f, 0.f}};
+                const uint32_t local = (uint32_t)__cvta_generic_to_shared(&s_slot[it & 1][rank]);
+                fps_st_remote(fps_mapa(local, (uint32_t)lane), s);
+            }
+        }
+        fps_cluster_barrier();                                 // also orders the block (all threads take part)
+        // final selection over the CS block results (same order in every CTA)
+        float gv = -2.f; int gi = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) {
+            const FpsSlot s = s_slot[it & 1][r];
+            if (s.v > gv || (s.v == gv && s.i < gi)) { gv = s.v; gi = s.i; cx = s.x; cy = s.y; cz = s.z; }
+        }
+        far = gi;
+    }
+    fps_cluster_barrier();                                     // nobody exits while a peer may still write into its shared memory
+}
+
+template <int CS>
+static int launch_fps_cluster(const float* xyz, int B, int N, int K, const int64_t* start, int64_t* out, cudaStream_t st) {
+    auto kern = fps_cluster_kernel<CS>;
+    if (CS > 8) DVM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(B * CS); cfg.blockDim = dim3(FPS_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DVM_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, K, start, out));
+    count_launch();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // graph tensors
 // ------------------------------------------------------------------------------------------------
 __global__ void gather_nodes_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ nodes_idx,
@@ -154,6 +269,12 @@ extern "C" int dvm_fps(const float* xyz, int B, int N, int K, const int64_t* sta
     DVM_CHECK_ARG(xyz && start && out, "dvm_fps: null pointer");
     DVM_CHECK_ARG(B > 0 && N > 0 && K > 0 && K <= N, "dvm_fps: bad sizes (B=%d N=%d K=%d)", B, N, K);
     cudaStream_t st = (cudaStream_t)stream;
+    // few big clouds: a cluster of CTAs per cloud (points in registers, results exchanged through distributed shared
+    // memory); many small clouds: one CTA each already fills the machine
+    if (N > FPS_THREADS * FPS_PPT && (long long)B * 8 <= 4 * kNumSM) {      // one CTA holds <= 8192 points in registers (1.1 us / iteration)
+        if (N <= 8 * FPS_THREADS * FPSC_PPT) return launch_fps_cluster<8>(xyz, B, N, K, start, out, st);
+        if (N <= 16 * FPS_THREADS * FPSC_PPT) return launch_fps_cluster<16>(xyz, B, N, K, start, out, st);
+    }
     if (N <= FPS_THREADS * FPS_PPT) {
         fps_kernel<true><<<B, FPS_THREADS, 0, st>>>(xyz, N, K, start, out, nullptr);
     } else {

@@ -596,3 +596,18 @@ def test_partial_loss_matches_reference():
         cos = float((s * r).sum() / (np.linalg.norm(s) * np.linalg.norm(r)))
         nrm = float(np.linalg.norm(gg)) / g["part_a40_gnorms"][nkey]
         assert cos >= 0.999 and abs(nrm - 1) <= 1e-2, (key, cos, nrm)
+
+
+def test_fps_cluster_kernel_matches_single_cta_kernel():
+    """Clouds > 8192 points take the thread-block-cluster FPS (distributed shared memory exchange); its node list must equal
+    the oracle's (= the reference's farthest_point_sample with the same start) bit for bit."""
+    ops = _ops()
+    from dv_matcher_b200 import synthetic
+    d = synthetic.make_batch(2, 12000, 12000, first_pair=5)
+    xyz = d["xyz1"]
+    xyz[0, 77] = xyz[0, 3]                                   # duplicate points: first-index tie-break
+    start = torch.tensor([5, 11999])
+    got = ops.fps(_cuda(xyz), 700, start).cpu().numpy()
+    for b in range(2):
+        ref = ogr.farthest_point_sample(xyz[b].numpy(), 700, int(start[b]))
+        assert (got[b] == ref).all()
