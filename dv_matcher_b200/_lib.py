@@ -47,6 +47,7 @@ SIGNATURES = {
     "dvm_arap_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 3),
     "dvm_gather_conv_fwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 2),
     "dvm_gather_conv_bwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 4),
+    "dvm_linear_act_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 
 PREC = {"fp32": 0, "f16": 1, "bf16": 2}

@@ -10,6 +10,7 @@ dvm_gather_conv_*), `Pi_12 @ feat2` (10-sparse, dvm_sparse_transfer_*), and -- i
 import torch
 import torch.nn as nn
 
+from . import ops
 from .geometry import gather_conv, index_points_idx
 from .maps import SparseSoftMap, _MapBase
 
@@ -32,6 +33,30 @@ class MLP(nn.Module):
 
     def forward(self, x):
         return self.linear(x)
+
+    def forward_tc(self, parts):
+        """Inference path: the concatenation `parts` (tensors [..., c_i]) goes straight into a staging buffer whose row pitch
+        is a multiple of 4 floats, every nn.Linear (+ its ELU) is one dvm_linear_act_fwd launch (tcgen05, 3xTF32)."""
+        lead = parts[0].shape[:-1]
+        K = sum(p.shape[-1] for p in parts)
+        x = torch.empty(*lead, (K + 3) // 4 * 4, dtype=torch.float32, device=parts[0].device)
+        c = 0
+        for p in parts:
+            x[..., c:c + p.shape[-1]] = p
+            c += p.shape[-1]
+        x = x.reshape(-1, x.shape[-1])
+        mods = list(self.linear)
+        i, cols = 0, K
+        while i < len(mods):
+            lin = mods[i]
+            elu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ELU) and mods[i + 1].alpha == 1.0
+            x = ops.linear_act_fwd(x, lin.weight, lin.bias, "elu" if elu else "none", x_cols=cols)
+            cols = None
+            i += 2 if elu else 1
+            if not elu and i < len(mods) and not isinstance(mods[i], nn.Linear):
+                x = mods[i](x)                                   # an activation other than ELU(1): stock torch
+                i += 1
+        return x.reshape(*lead, x.shape[-1])
 
 
 class Deformer(nn.Module):
@@ -70,4 +95,8 @@ class Deformer(nn.Module):
         return self._decode(index_points_idx(verts1, fps1), st_feat1, index_points_idx(verts12, fps1), st_feat2)
 
     def _decode(self, st_vts1, st_feat1, st_vts12, st_feat2):
-        return self.deformation_decoder_layer(torch.cat([st_vts1, st_feat1, st_vts12, st_feat2], dim=-1))
+        parts = [st_vts1, st_feat1, st_vts12, st_feat2]
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in parts) or any(q.requires_grad for q in self.parameters()))
+        if parts[0].is_cuda and not needs_grad:
+            return self.deformation_decoder_layer.forward_tc(parts)
+        return self.deformation_decoder_layer(torch.cat(parts, dim=-1))           # training: autograd through torch's Linear

@@ -278,3 +278,32 @@ def gather_conv_bwd(feat, idx, weight, d_out):
     check(lib.dvm_gather_conv_bwd(ptr(feat), ptr(idx), ptr(w), ptr(d_out), B, N, R, C, k, ptr(d_feat), ptr(d_w), ptr(d_b), stream_ptr()),
           "dvm_gather_conv_bwd")
     return d_feat, d_w, d_b
+
+
+def linear_act_fwd(x, weight, bias, act="none", x_cols=None):
+    """act(x @ weight.T + bias) on tensor cores with fp32-equivalent accuracy (dvm_linear_act_fwd; nn.Linear weight layout).
+
+    x: [..., K] fp32 (last-dim stride 1, a row pitch that is a multiple of 4 floats -- e.g. a padded staging buffer
+    viewed through `x_cols`: x [rows, pitch] with x_cols = K valid columns)."""
+    lib = _lib.load()
+    require_device(x)
+    K = x.shape[-1] if x_cols is None else x_cols
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype != torch.float32 or x2.stride(1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16:
+        xp = torch.empty(x2.shape[0], (K + 3) // 4 * 4, dtype=torch.float32, device=x.device)
+        xp[:, :K] = x2[:, :K]
+        x2 = xp
+    N, Kw = weight.shape
+    if Kw != K:
+        raise ValueError(f"linear_act_fwd: weight is [{N},{Kw}] but x has {K} columns")
+    w = weight.detach()
+    if w.dtype != torch.float32 or w.stride(1) != 1 or w.stride(0) % 4 or w.data_ptr() % 16:
+        wp = torch.empty(N, (K + 3) // 4 * 4, dtype=torch.float32, device=x.device)
+        wp[:, :K] = w
+        w = wp
+    b = f32c(bias.detach()) if bias is not None else None
+    out = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
+    check(lib.dvm_linear_act_fwd(x2.data_ptr(), x2.shape[0], K, x2.stride(0), w.data_ptr(), w.stride(0), ptr(b), N, {"none": 0, "elu": 1}[act],
+                                 ptr(out), N, stream_ptr()), "dvm_linear_act_fwd")
+    return out.reshape(*lead, N)

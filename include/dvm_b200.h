@@ -167,6 +167,14 @@ int dvm_gather_conv_fwd(const float* feat, const int64_t* idx, const float* W, c
 int dvm_gather_conv_bwd(const float* feat, const int64_t* idx, const float* W, const float* dOut,
                         int B, int N, int R, int C, int k, float* dFeat, float* dW, float* dBias, void* stream);
 
+/* One layer of the Deformer's decoder MLP (models/model.py:433-452: nn.Linear + nn.ELU; called at :476-477):
+ *   out[r, n] = act( sum_k x[r,k] W[n,k] + bias[n] ),  x[rows][x_pitch] (K used), W[N][w_pitch] (nn.Linear layout),
+ *   act 0 = identity, 1 = ELU(alpha=1).  tcgen05 tensor cores with 3xTF32 operand splitting (fp32-equivalent: relative
+ *   error ~1e-6 of |x||W| per output, like an fp32 SGEMM).  x_pitch, w_pitch: multiples of 4 floats; pointers 16-byte
+ *   aligned; bias may be NULL.  Forward only (training keeps torch's autograd Linear). */
+int dvm_linear_act_fwd(const float* x, long long rows, int K, int x_pitch, const float* W, int w_pitch, const float* bias,
+                       int N, int act, float* out, int out_pitch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
