@@ -321,24 +321,42 @@ __device__ __forceinline__ void rescore_emit(const FinalizeArgs& a, int g, int b
     }
     float my_d2 = INFINITY; int my_idx = 0x7fffffff;
     const float* Yb = a.Y + (size_t)b * a.M * a.C;
-    for (int s = 0; s < n_max; ++s) {
-        const int j = __shfl_sync(0xffffffffu, sel_idx, s);
-        if (j < 0) break;                                             // uniform
-        float acc = 0.f;
+    for (int s0 = 0; s0 < n_max; s0 += 16) {                              // 16 candidates per round
+        if (__shfl_sync(0xffffffffu, sel_idx, s0) < 0) break;             // uniform: the selection is dense from lane 0
+        float acc[16];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int c = 4 * lane + 128 * t;
-            if (c < a.C) {
-                const float4 yv = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)j * a.C + c));
-                float d;
-                d = xv[t].x - yv.x; acc = fmaf(d, d, acc);
-                d = xv[t].y - yv.y; acc = fmaf(d, d, acc);
-                d = xv[t].z - yv.z; acc = fmaf(d, d, acc);
-                d = xv[t].w - yv.w; acc = fmaf(d, d, acc);
+        for (int s = 0; s < 16; ++s) {
+            const int j = __shfl_sync(0xffffffffu, sel_idx, s0 + s);
+            const float* yr = Yb + (size_t)(j < 0 ? 0 : j) * a.C;        // absent: any valid row, the sum is dropped below
+            float v = 0.f;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int c = 4 * lane + 128 * t;
+                if (c < a.C) {
+                    const float4 yv = __ldg(reinterpret_cast<const float4*>(yr + c));
+                    float d;
+                    d = xv[t].x - yv.x; v = fmaf(d, d, v);
+                    d = xv[t].y - yv.y; v = fmaf(d, d, v);
+                    d = xv[t].z - yv.z; v = fmaf(d, d, v);
+                    d = xv[t].w - yv.w; v = fmaf(d, d, v);
+                }
             }
+            acc[s] = v;
         }
-        acc = warp_sum(acc);
-        if (lane == s) { my_d2 = acc; my_idx = j; }
+        // 16 butterfly sums at once: at every step a lane keeps one half of its values and trades the other half with
+        // its partner -- the same pairing and order as warp_sum (bit-identical totals), 16 shuffles instead of 80
+        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+        float u8[8], u4[4], u2[2];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) u8[c] = (b16 ? acc[c + 8] : acc[c]) + __shfl_xor_sync(0xffffffffu, b16 ? acc[c] : acc[c + 8], 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) u4[c] = (b8 ? u8[c + 4] : u8[c]) + __shfl_xor_sync(0xffffffffu, b8 ? u8[c] : u8[c + 4], 8);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) u2[c] = (b4 ? u4[c + 2] : u4[c]) + __shfl_xor_sync(0xffffffffu, b4 ? u4[c] : u4[c + 2], 4);
+        float u1 = (b2 ? u2[1] : u2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u2[0] : u2[1], 2);
+        u1 += __shfl_xor_sync(0xffffffffu, u1, 1);                        // lanes 2c, 2c+1 hold candidate s0 + c
+        const float mine = __shfl_sync(0xffffffffu, u1, 2 * (lane & 15));
+        if ((lane & ~15) == s0 && sel_idx >= 0) { my_d2 = mine; my_idx = sel_idx; }
     }
 
     // ---- rank the exact scores: (d2, idx) lexicographic
@@ -402,6 +420,16 @@ __device__ __forceinline__ void rescore_emit(const FinalizeArgs& a, int g, int b
     }
 }
 
+// float <-> unsigned with the same ordering (-0 is folded onto +0 so that equal keys tie on the index)
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+    unsigned u = __float_as_uint(f);
+    if (u == 0x80000000u) u = 0u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_ordered(unsigned o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
 template <bool kSoft>
 __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(FinalizeArgs a) {
     const int lane = threadIdx.x & 31;
@@ -419,16 +447,15 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
     const int E = P * KC;                       // <= 128
     const float a2 = a.alpha * kLog2e;
 
-    // ---- load the partial lists: entry e = lane + 32 q
-    float ek[4]; int ei[4]; bool taken[4];
+    // ---- load the partial lists: entry e = lane + 32 q, as (order-preserving key bits, index) with "absent" = ~0
+    unsigned eo[4]; int ei[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int e = lane + 32 * q;
-        ek[q] = INFINITY; ei[q] = -1; taken[q] = true;
+        eo[q] = 0xffffffffu; ei[q] = 0x7fffffff;
         if (e < E) {
-            ek[q] = a.cb.key[(size_t)g * E + e];
-            ei[q] = a.cb.idx[(size_t)g * E + e];
-            taken[q] = !(ei[q] >= 0);
+            const int j = a.cb.idx[(size_t)g * E + e];
+            if (j >= 0) { eo[q] = f32_ordered(a.cb.key[(size_t)g * E + e]); ei[q] = j; }
         }
     }
     float l_tot = 0.f, r_star = INFINITY;
@@ -442,26 +469,22 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
         l_tot = warp_sum(t);
     }
 
-    // ---- select the KC best of the union by (key, idx)
+    // ---- select the KC best of the union by (key, idx): every lane keeps its (up to 4) entries sorted, one round =
+    //      two warp-wide integer min reductions (redux.sync) over the lanes' heads; the owner pops its head
+#define DVM_CSWAP(i, j) { const bool sw = eo[j] < eo[i] || (eo[j] == eo[i] && ei[j] < ei[i]); \
+        const unsigned tk = sw ? eo[j] : eo[i]; const int ti = sw ? ei[j] : ei[i]; \
+        eo[j] = sw ? eo[i] : eo[j]; ei[j] = sw ? ei[i] : ei[j]; eo[i] = tk; ei[i] = ti; }
+    DVM_CSWAP(0, 1) DVM_CSWAP(2, 3) DVM_CSWAP(0, 2) DVM_CSWAP(1, 3) DVM_CSWAP(1, 2)
+#undef DVM_CSWAP
     float sel_key = INFINITY; int sel_idx = -1;     // lane s (< KC) holds the s-th selected
     for (int s = 0; s < KC; ++s) {
-        float bk = INFINITY; int bi = 0x7fffffff; int bq = -1;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (!taken[q] && kv_less(ek[q], ei[q], bk, bi)) { bk = ek[q]; bi = ei[q]; bq = q; }
-        float wk = bk; int wi = bi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ok = __shfl_xor_sync(0xffffffffu, wk, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-            if (kv_less(ok, oi, wk, wi)) { wk = ok; wi = oi; }
+        const unsigned wk = __reduce_min_sync(0xffffffffu, eo[0]);
+        if (wk == 0xffffffffu) break;                                 // union exhausted (uniform)
+        const int wi = __reduce_min_sync(0xffffffffu, eo[0] == wk ? ei[0] : 0x7fffffff);
+        if (eo[0] == wk && ei[0] == wi) {                             // the owner retires it (indices are unique)
+            eo[0] = eo[1]; ei[0] = ei[1]; eo[1] = eo[2]; ei[1] = ei[2]; eo[2] = eo[3]; ei[2] = ei[3]; eo[3] = 0xffffffffu; ei[3] = 0x7fffffff;
         }
-        if (wi == 0x7fffffff) break;                                  // union exhausted (uniform)
-        if (bq >= 0 && bk == wk && bi == wi) {                        // the owner retires it (indices are unique)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (q == bq) taken[q] = true;
-        }
-        if (lane == s) { sel_key = wk; sel_idx = wi; }
+        if (lane == s) { sel_key = f32_from_ordered(wk); sel_idx = wi; }
     }
     float key16 = __shfl_sync(0xffffffffu, sel_key, KC - 1);
     {                                                                 // discard bounds of the partial lists
@@ -474,7 +497,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
         float t = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (!taken[q]) t += exp2f(-a2 * (sqrtf(ek[q]) - r_star));
+            if (eo[q] != 0xffffffffu) t += exp2f(-a2 * (sqrtf(f32_from_ordered(eo[q])) - r_star));
         l_tot += warp_sum(t);
     }
 
