@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
 constexpr int RESC_MAX = 4096;       // flagged rows handled by the rescue scan; more -> fp32 candidate pass
 constexpr int RESC_CAP = 32;         // listed columns per row; more (mass ties) -> fp32 pass for that row
 constexpr int RESC_NCH_MAX = 2048;   // column chunks (M <= 262144 for the rescue scan; beyond: fp32 pass)
-constexpr int RESC_ROWS = 8;         // flagged rows per group
+constexpr int RESC_ROWS = 32;        // flagged rows per group (a thread = 8 rows x 2 columns)
 
 constexpr int RESC_CHUNK = 128;      // columns per CTA: the Y chunk is staged ONCE in shared memory (coalesced) and reused
                                      // for every flagged row of the batch element
@@ -557,7 +557,7 @@ rescue_scan_kernel(const float* __restrict__ X, const float* __restrict__ Y, int
     __shared__ int s_slots[RESC_MAX];
     __shared__ int s_n;
     __shared__ float s_thr[RESC_ROWS], s_ref[RESC_ROWS];
-    __shared__ float s_part[4][RESC_ROWS];
+    __shared__ float s_part[2][RESC_ROWS];
     const int count = *flag_count;
     if (count == 0 || count > RESC_MAX) return;
     const int b = blockIdx.y, ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -576,9 +576,8 @@ rescue_scan_kernel(const float* __restrict__ X, const float* __restrict__ Y, int
         const int rr = e / c4, cc = e - rr * c4;
         *reinterpret_cast<float4*>(Ys + rr * ld + cc * 4) = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)rr * C) + cc);
     }
-    const int col = tid & (RESC_CHUNK - 1);                  // this thread's column of the chunk
-    const int rh = tid >> 7;                                 // ... and its half of the row group (rows rh*4 .. +3)
-    const bool col_ok = col < ncol;
+    const int col = tid & 63;                                // this thread's columns of the chunk: col, col + 64
+    const int rg = tid >> 6;                                 // ... and its quarter of the row group (rows rg*8 .. +7)
     for (int g0 = 0; g0 < n; g0 += RESC_ROWS) {
         __syncthreads();
         for (int e = tid; e < RESC_ROWS * c4; e += 256) {
@@ -593,45 +592,59 @@ rescue_scan_kernel(const float* __restrict__ X, const float* __restrict__ Y, int
             s_ref[tid] = ok ? flag_r[s_slots[g0 + tid]] : 0.f;
         }
         __syncthreads();
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* yp = Ys + col * ld;
-        const float* xp = xs + (rh * 4) * C;
-        for (int k = 0; k < C; k += 4) {
-            const float4 yv = *reinterpret_cast<const float4*>(yp + k);
+        if (g0 + rg * 8 >= n) continue;                      // warp-uniform (and no barrier below for hard maps) ...
+        float acc[8][2];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = 0.f;
+        const float* yp = Ys + col * ld;
+        const float* xp = xs + (rg * 8) * C;
+        for (int k = 0; k < C; k += 4) {
+            const float4 y0 = *reinterpret_cast<const float4*>(yp + k);
+            const float4 y1 = *reinterpret_cast<const float4*>(yp + 64 * ld + k);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
                 const float4 xv = *reinterpret_cast<const float4*>(xp + r * C + k);      // warp-broadcast
                 float d;
-                d = xv.x - yv.x; acc[r] = fmaf(d, d, acc[r]);
-                d = xv.y - yv.y; acc[r] = fmaf(d, d, acc[r]);
-                d = xv.z - yv.z; acc[r] = fmaf(d, d, acc[r]);
-                d = xv.w - yv.w; acc[r] = fmaf(d, d, acc[r]);
+                d = xv.x - y0.x; acc[r][0] = fmaf(d, d, acc[r][0]);
+                d = xv.y - y0.y; acc[r][0] = fmaf(d, d, acc[r][0]);
+                d = xv.z - y0.z; acc[r][0] = fmaf(d, d, acc[r][0]);
+                d = xv.w - y0.w; acc[r][0] = fmaf(d, d, acc[r][0]);
+                d = xv.x - y1.x; acc[r][1] = fmaf(d, d, acc[r][1]);
+                d = xv.y - y1.y; acc[r][1] = fmaf(d, d, acc[r][1]);
+                d = xv.z - y1.z; acc[r][1] = fmaf(d, d, acc[r][1]);
+                d = xv.w - y1.w; acc[r][1] = fmaf(d, d, acc[r][1]);
             }
         }
-        float mass[4] = {0.f, 0.f, 0.f, 0.f};
+        float mass[8];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int rr = rh * 4 + r;
-            if (col_ok && g0 + rr < n) {
-                if (acc[r] <= s_thr[rr]) {
-                    const int slot = s_slots[g0 + rr];
-                    const int q = atomicAdd(resc_cnt + slot, 1);
-                    if (q < RESC_CAP) resc_idx[(size_t)slot * RESC_CAP + q] = c0 + col;
-                } else if (kSoft) {
-                    mass[r] = exp2f(-a2 * (sqrtf(acc[r]) - s_ref[rr]));
+        for (int r = 0; r < 8; ++r) {
+            const int rr = rg * 8 + r;
+            mass[r] = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (col + 64 * h < ncol && g0 + rr < n) {
+                    if (acc[r][h] <= s_thr[rr]) {
+                        const int slot = s_slots[g0 + rr];
+                        const int q = atomicAdd(resc_cnt + slot, 1);
+                        if (q < RESC_CAP) resc_idx[(size_t)slot * RESC_CAP + q] = c0 + col + 64 * h;
+                    } else if (kSoft) {
+                        mass[r] += exp2f(-a2 * (sqrtf(acc[r][h]) - s_ref[rr]));
+                    }
                 }
             }
         }
         if (kSoft) {
-            // deterministic: lanes -> warp sum, then the 4 warps of a row half in fixed order
+            // deterministic: lanes -> warp sum, then the 2 warps of a row quarter in fixed order (named barrier per quarter:
+            // quarters without rows skipped the pass)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < 8; ++r) {
                 const float v = warp_sum(mass[r]);
-                if (lane == 0) s_part[wid & 3][rh * 4 + r] = v;
+                if (lane == 0) s_part[wid & 1][rg * 8 + r] = v;
             }
-            __syncthreads();
-            if (tid < RESC_ROWS && g0 + tid < n)
-                resc_mass[(size_t)s_slots[g0 + tid] * nch + ch] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+            asm volatile("bar.sync %0, 64;" ::"r"(rg + 1) : "memory");
+            const int t64 = tid & 63;
+            if (t64 < 8 && g0 + rg * 8 + t64 < n)
+                resc_mass[(size_t)s_slots[g0 + rg * 8 + t64] * nch + ch] = s_part[0][rg * 8 + t64] + s_part[1][rg * 8 + t64];
         }
     }
 }
