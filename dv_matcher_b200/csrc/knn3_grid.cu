@@ -354,8 +354,12 @@ knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHea
         const int xlo = max(cx - s, 0), xhi = min(cx + s, g.nx - 1);
         const int wy = yhi - ylo + 1;
         const int nrows = (zhi - zlo + 1) * wy;
+        // (z, y) of row r = sub + i * GRID_LPQ, advanced without a division per row
+        const int step_z = GRID_LPQ / wy, step_y = GRID_LPQ % wy;
+        int z = zlo + sub / wy - step_z, y = ylo + sub % wy - step_y;
         for (int r = sub; r < nrows; r += GRID_LPQ) {
-            const int z = zlo + r / wy, y = ylo + r % wy;
+            z += step_z; y += step_y;
+            if (y > yhi) { y -= wy; ++z; }
             const int2 ext = __ldg(rowx + z * g.ny + y);       // occupied cells of the row (L1-resident table)
             int x0 = max(xlo, ext.x), x1 = min(xhi, ext.y);
             if (x0 > x1) continue;                             // nothing of the row inside the box

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Executed-instruction and stall-sample share per CUDA source line of one kernel in an .ncu-rep (needs -lineinfo + --import-source on).
-    python tools/ncu_lines.py rep kernel_regex [top]"""
+    python tools/ncu_lines.py rep kernel_regex [top] [skip]     (skip = number of matching launches to skip)"""
 import collections, csv, io, subprocess, sys
 rep, rx = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + rx, "-c", "1"], capture_output=True, text=True).stdout
+skip = sys.argv[4] if len(sys.argv) > 4 else "0"
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + rx, "-s", skip, "-c", "1"], capture_output=True, text=True).stdout
 cur = None; agg = collections.Counter(); smp = collections.Counter(); text = {}; tot = ts = 0
 for r in csv.reader(io.StringIO(src)):
     if not r: continue
