@@ -228,7 +228,17 @@ __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase
     }
 }
 
-// kPrime: priming pass -- strided tile sample, K = KP, hard mode, only outputs are thr_global / rmin_global.
+// priming pass: the scanner thread keeps the KP smallest CHUNK MINIMA it has seen in a sorted register list (a branch-free
+// insertion).  The KP-th smallest chunk minimum is a key with at least KP keys <= it, i.e. a valid bound for the row's KP-th
+// smallest key -- and almost as tight as the KP-th smallest key itself (the few smallest keys of a row sit in distinct
+// chunks) -- so the priming pass needs no queues and no consumers: its cost is the min-tree.
+__device__ __forceinline__ void prime_chunk(const float (&k)[TC_CHUNK], float (&pl)[8]) {
+    float c = min16(k);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { const float lo = fminf(pl[t], c); c = fmaxf(pl[t], c); pl[t] = lo; }
+}
+
+// kPrime: priming pass -- strided tile sample, hard mode, only outputs are thr_global / rmin_global.
 template <bool kSoft, bool kPrime>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXe,
@@ -390,6 +400,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * TC_BN + half * 64;
         float priv = INFINITY;
+        float pl[KP];
+#pragma unroll
+        for (int t = 0; t < KP; ++t) pl[t] = INFINITY;
 #pragma unroll 1
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
@@ -403,18 +416,23 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_issue(taddr, ka);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + TC_CHUNK, kb);
-            scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
             tc_ld16_wait(kb);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
-            scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
-            scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
             tc_ld16_wait(kb);
             tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
-            scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+        }
+        if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
+            float2* L = lists + (sb * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + half * KP;
+#pragma unroll
+            for (int t = 0; t < KP; ++t) L[t] = make_float2(pl[t], 0.f);
         }
         __syncwarp();
         if (lane == 0) {
@@ -432,6 +450,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cw * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cw * sizeof(QCtl);
         unsigned head = 0;
+        if (kPrime) {                                        // nothing is queued: wait for the two scanner warps of these rows
+            while (lds_u32_acquire(ctl_a + 8) != 2u) __nanosleep(200);
+        } else
         for (;;) {
             const unsigned g = head + (unsigned)lane;
             const uint32_t ea = q_a + (g % Q_CAP) * Q_ENTRY;
@@ -535,8 +556,14 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const float xx = xx_s[rl];
                 const float2* L = lists + rl * LIST_STRIDE;
                 if (kPrime) {
-                    float w = -INFINITY, m = INFINITY;
-                    for (int t = 0; t < K; ++t) { w = fmaxf(w, L[t].x); m = fminf(m, L[t].x); }
+                    // merge the two sorted lists of chunk minima (column halves): KP-th smallest of the union, and the minimum
+                    int i = 0, j = KP;
+                    float w = INFINITY;
+                    for (int t = 0; t < KP; ++t) {
+                        const float a = i < KP ? L[i].x : INFINITY, c = j < 2 * KP ? L[j].x : INFINITY;
+                        if (a <= c) { w = a; ++i; } else { w = c; ++j; }
+                    }
+                    const float m = fminf(L[0].x, L[KP].x);
                     if (w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
                     if (m < LIST_EMPTY) atomicMin(p.rmin_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, m, xx), 0.f)));
                 } else {
