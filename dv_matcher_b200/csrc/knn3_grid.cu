@@ -15,6 +15,8 @@
 namespace dvm {
 
 constexpr int GRID_THREADS = 256;
+constexpr int GRID_QTHREADS = 128;       // query kernel: small blocks -- the work per query varies a lot (dense regions, far queries), and
+                                         // the last wave of big blocks left half of the SMs idle
 
 constexpr int GRID_COARSE = 8;    // a coarse cell = 8 x 8 x 8 fine cells: used to skip empty space around far queries
 constexpr int GRID_COARSE_MAX = 1 << 16;
@@ -309,12 +311,12 @@ __device__ __forceinline__ void scan_span(GList<T, K>& list, const float4* __res
 // kSelf: Q is the reference cloud itself -> thread t handles the t-th point in CELL-SORTED order, so the lanes of a
 // warp are spatial neighbours (same rows, same spans: little divergence, L1-friendly) and write to their original row.
 template <typename T, int K, int GRID_LPQ, bool kSelf>
-__global__ void __launch_bounds__(GRID_THREADS)
+__global__ void __launch_bounds__(GRID_QTHREADS)
 knn3_grid_kernel(const float* __restrict__ Q, int N, int M, int k, const GridHeader* __restrict__ hdr, int stride,
                  const int* __restrict__ start, const int* __restrict__ cstart, const int2* __restrict__ rowx_all,
                  const float4* __restrict__ sorted, const int* __restrict__ qorder, int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ d2f, double* __restrict__ d2d) {
     const int b = blockIdx.y;
-    int q = blockIdx.x * (GRID_THREADS / GRID_LPQ) + threadIdx.x / GRID_LPQ;
+    int q = blockIdx.x * (GRID_QTHREADS / GRID_LPQ) + threadIdx.x / GRID_LPQ;
     const int sub = threadIdx.x % GRID_LPQ;
     const bool live = q < N;
     const GridHeader g = hdr[b];
@@ -519,9 +521,9 @@ size_t knn3_grid_workspace_bytes(int B, int N, int M) { return grid_ws_layout(nu
 template <typename T, int K, int LPQ = 1>
 static void launch_query(const float* Q, bool self, const int* qorder, int B, int N, int M, int k, const GridWs& w,
                          int64_t* idx64, int32_t* idx32, float* d2f, double* d2d, cudaStream_t st) {
-    dim3 grid(ceil_div(N, GRID_THREADS / LPQ), B);
-    if (self) knn3_grid_kernel<T, K, LPQ, true><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, qorder, idx64, idx32, d2f, d2d);
-    else      knn3_grid_kernel<T, K, LPQ, false><<<grid, GRID_THREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, qorder, idx64, idx32, d2f, d2d);
+    dim3 grid(ceil_div(N, GRID_QTHREADS / LPQ), B);
+    if (self) knn3_grid_kernel<T, K, LPQ, true><<<grid, GRID_QTHREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, qorder, idx64, idx32, d2f, d2d);
+    else      knn3_grid_kernel<T, K, LPQ, false><<<grid, GRID_QTHREADS, 0, st>>>(Q, N, M, k, w.hdr, w.stride, w.start, w.cstart, w.rowx, w.sorted, qorder, idx64, idx32, d2f, d2d);
 }
 
 // k nearest neighbours of Q[B,N,3] in R[B,M,3] through a grid built on R (inside ws)

@@ -39,7 +39,8 @@ constexpr int TC_EXT_BYTES = 128 * 32;         // one 128-row x 16-element K blo
 constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_CHUNK = 16;               // columns per min-tree
 constexpr int TC_PRIME_STRIDE = 16;        // priming pass: every 16th tile
-constexpr int TC_PRIME_MIN_TILES = 128;     // ... when the sweep has at least this many tiles (M >= 16k)
+constexpr int TC_PRIME_MIN_TILES = 128;
+constexpr int TC_PREP_ROWS = 32;           // rows per block of the operand preparation (8 warps x 4 rows)     // ... when the sweep has at least this many tiles (M >= 16k)
 
 
 // ------------------------------------------------------------------------------------------------
@@ -64,62 +65,76 @@ tc_prep_kernel(const float* __restrict__ src, int rows_per_b, int rows_alloc, in
                float* __restrict__ err_row /* X only */, float* __restrict__ err_max /* [B], Y only */,
                float* __restrict__ yy_max /* [B], Y only */) {
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int b = blockIdx.y;
-    if (r >= rows_alloc) return;
     const int Ktot = Cpad + TC_KEXT;
-    uint16_t* d = dst + ((size_t)b * rows_alloc + r) * Ktot;
     float dummy;
-    if (r >= rows_per_b) {                       // Y padding row
-        for (int c = lane; c < Ktot; c += 32) d[c] = (c == Cpad) ? Cvt16<kBF16>::bits(INFINITY, dummy) : (uint16_t)0;
-        return;
-    }
-    const float* s = src + ((size_t)b * rows_per_b + r) * C;
-    float n2 = 0.f, e2 = 0.f;
-    for (int c = lane * 4; c < Cpad; c += 128) {             // C % 4 == 0: float4 in, 4 x 16-bit (8 bytes) out
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < C) v = __ldg(reinterpret_cast<const float4*>(s + c));
-        const float in[4] = {v.x, v.y, v.z, v.w};
-        uint16_t o[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float x = kIsY ? -in[t] : in[t];
-            float vr;
-            o[t] = Cvt16<kBF16>::bits(x, vr);
-            n2 = fmaf(vr, vr, n2);
-            const float e = x - vr;                          // +-inf when the value overflows the 16-bit format
-            e2 = fmaf(e, e, e2);
+    float blk_err = 0.f, blk_yy = 0.f;           // Y: maxima over this warp's rows (one atomic pair per BLOCK at the end:
+                                                 // a per-row atomicMax on one address serialises 200k updates)
+    for (int rr = 0; rr < TC_PREP_ROWS; rr += 8) {
+        const int r = blockIdx.x * TC_PREP_ROWS + rr + (threadIdx.x >> 5);
+        if (r >= rows_alloc) break;
+        uint16_t* d = dst + ((size_t)b * rows_alloc + r) * Ktot;
+        if (r >= rows_per_b) {                       // Y padding row
+            for (int c = lane; c < Ktot; c += 32) d[c] = (c == Cpad) ? Cvt16<kBF16>::bits(INFINITY, dummy) : (uint16_t)0;
+            continue;
         }
-        uint2 pk;
-        pk.x = (uint32_t)o[0] | ((uint32_t)o[1] << 16);
-        pk.y = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
-        *reinterpret_cast<uint2*>(d + c) = pk;
-    }
-    n2 = warp_sum(n2); e2 = warp_sum(e2);
-    if (lane < TC_KEXT) {
-        uint16_t w = 0;
-        if (!kIsY) {
-            if (lane < 3) w = Cvt16<kBF16>::bits(1.0f, dummy);
-        } else {
-            const float h = 0.5f * n2;
-            float h0, h1, h2;
-            const uint16_t b0 = Cvt16<kBF16>::bits(h, h0);
-            const uint16_t b1 = Cvt16<kBF16>::bits(h - h0, h1);
-            const uint16_t b2 = Cvt16<kBF16>::bits((h - h0) - h1, h2);
-            w = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : (uint16_t)0;
+        const float* s = src + ((size_t)b * rows_per_b + r) * C;
+        float n2 = 0.f, e2 = 0.f;
+        for (int c = lane * 4; c < Cpad; c += 128) {             // C % 4 == 0: float4 in, 4 x 16-bit (8 bytes) out
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C) v = __ldg(reinterpret_cast<const float4*>(s + c));
+            const float in[4] = {v.x, v.y, v.z, v.w};
+            uint16_t o[4];
+    #pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float x = kIsY ? -in[t] : in[t];
+                float vr;
+                o[t] = Cvt16<kBF16>::bits(x, vr);
+                n2 = fmaf(vr, vr, n2);
+                const float e = x - vr;                          // +-inf when the value overflows the 16-bit format
+                e2 = fmaf(e, e, e2);
+            }
+            uint2 pk;
+            pk.x = (uint32_t)o[0] | ((uint32_t)o[1] << 16);
+            pk.y = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
+            *reinterpret_cast<uint2*>(d + c) = pk;
         }
-        d[Cpad + lane] = w;
+        n2 = warp_sum(n2); e2 = warp_sum(e2);
+        if (lane < TC_KEXT) {
+            uint16_t w = 0;
+            if (!kIsY) {
+                if (lane < 3) w = Cvt16<kBF16>::bits(1.0f, dummy);
+            } else {
+                const float h = 0.5f * n2;
+                float h0, h1, h2;
+                const uint16_t b0 = Cvt16<kBF16>::bits(h, h0);
+                const uint16_t b1 = Cvt16<kBF16>::bits(h - h0, h1);
+                const uint16_t b2 = Cvt16<kBF16>::bits((h - h0) - h1, h2);
+                w = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : (uint16_t)0;
+            }
+            d[Cpad + lane] = w;
+        }
+        {
+            float e = sqrtf(e2) * 1.0001f;
+            if (kIsY) {
+                float hb; Cvt16<kBF16>::bits(0.5f * n2, hb);
+                if (!(hb < INFINITY) || !(e < INFINITY)) e = INFINITY;          // |y|^2/2 not representable: nothing is certified
+                blk_err = fmaxf(blk_err, e); blk_yy = fmaxf(blk_yy, n2);        // NaN-free: e, n2 >= 0 or +inf
+            } else if (lane == 0) {
+                xx[(size_t)b * rows_per_b + r] = n2;
+                err_row[(size_t)b * rows_per_b + r] = e;
+            }
+        }
     }
-    if (lane == 0) {
-        float e = sqrtf(e2) * 1.0001f;
-        if (kIsY) {
-            float hb; Cvt16<kBF16>::bits(0.5f * n2, hb);
-            if (!(hb < INFINITY) || !(e < INFINITY)) e = INFINITY;          // |y|^2/2 not representable: nothing is certified
-            atomicMax(reinterpret_cast<int*>(err_max + b), __float_as_int(e));   // e >= 0: int order == float order
-            atomicMax(reinterpret_cast<int*>(yy_max + b), __float_as_int(n2));
-        } else {
-            xx[(size_t)b * rows_per_b + r] = n2;
-            err_row[(size_t)b * rows_per_b + r] = e;
+    if (kIsY) {
+        __shared__ float s_e[8], s_y[8];
+        if (lane == 0) { s_e[threadIdx.x >> 5] = blk_err; s_y[threadIdx.x >> 5] = blk_yy; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float e = 0.f, y = 0.f;
+            for (int w = 0; w < 8; ++w) { e = fmaxf(e, s_e[w]); y = fmaxf(y, s_y[w]); }
+            atomicMax(reinterpret_cast<int*>(err_max + b), __float_as_int(e));   // values >= 0: int order == float order
+            atomicMax(reinterpret_cast<int*>(yy_max + b), __float_as_int(y));
         }
     }
 }
@@ -674,7 +689,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     DVM_CUDA(cudaMemsetAsync(err_ymax, 0, (size_t)B * sizeof(float), st));
     DVM_CUDA(cudaMemsetAsync(w.yy_max, 0, (size_t)B * sizeof(float), st));
     {
-        dim3 gx(ceil_div(N, 8), B), gy(ceil_div(w.Mpad, 8), B);
+        dim3 gx(ceil_div(N, TC_PREP_ROWS), B), gy(ceil_div(w.Mpad, TC_PREP_ROWS), B);
         if (bf16) {
             tc_prep_kernel<true, false><<<gx, 256, 0, st>>>(X, N, N, C, w.Cpad, w.Xh, w.xx, err_x, nullptr, nullptr);
             DVM_LAUNCH_CHECK();
