@@ -20,6 +20,10 @@ constexpr int GRID_QTHREADS = 128;       // query kernel: small blocks -- the wo
 
 constexpr int GRID_COARSE = 8;    // a coarse cell = 8 x 8 x 8 fine cells: used to skip empty space around far queries
 constexpr int GRID_COARSE_MAX = 1 << 16;
+// cell edge = GRID_H_SCALE * sqrt(bounding-box surface / M): ~4 points per occupied cell of a surface cloud.  Measured at
+// N = 50k (xyz 10-NN | Chamfer | match+deform step, ms): scale 1.0: 0.38 | 0.54 | 7.56, 2.0: 0.29 | 0.49 | 7.34, 3.0: 0.34 | 0.48 | 7.55
+// -- with one point per cell the first 3x3x3 box rarely holds 10 points and every row of cells costs ~40 instructions.
+constexpr float GRID_H_SCALE = 2.0f;
 
 struct GridHeader {          // one per cloud, written by grid_setup_kernel
     float x0, y0, z0, h, inv_h;
@@ -28,7 +32,7 @@ struct GridHeader {          // one per cloud, written by grid_setup_kernel
 };
 
 __global__ void __launch_bounds__(1024)
-grid_setup_kernel(const float* __restrict__ R, int M, int ncell_max, GridHeader* __restrict__ hdr) {
+grid_setup_kernel(const float* __restrict__ R, int M, int ncell_max, float h_scale, GridHeader* __restrict__ hdr) {
     __shared__ float s_lo[3][32], s_hi[3][32];
     const int b = blockIdx.x;
     const float* P = R + (size_t)b * M * 3;
@@ -57,7 +61,7 @@ grid_setup_kernel(const float* __restrict__ R, int M, int ncell_max, GridHeader*
         for (int c = 0; c < 3; ++c) { ext[c] = hi[c] - lo[c]; if (!(ext[c] > 0.f) || !(ext[c] < INFINITY)) ext[c] = 0.f; }
         const float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
         float area = 2.f * (ext[0] * ext[1] + ext[1] * ext[2] + ext[0] * ext[2]);
-        float h = sqrtf(area / (float)M);
+        float h = h_scale * sqrtf(area / (float)M);
         if (!(h > emax * 1e-4f)) h = emax * 1e-4f;        // degenerate (collinear / coincident) clouds
         if (!(h > 0.f)) h = 1.f;
         int nx, ny, nz;
@@ -532,7 +536,7 @@ int launch_knn3_grid(const float* Q, const float* R, int B, int N, int M, int k,
     GridWs w;
     const size_t need = grid_ws_layout(wsp, ws_bytes, B, N, M, &w);
     if (!wsp || need > ws_bytes) { set_error("knn3 grid: workspace too small (%zu < %zu)", ws_bytes, need); return DVM_ERR_WORKSPACE; }
-    grid_setup_kernel<<<B, 1024, 0, st>>>(R, M, w.ncell_max, w.hdr);
+    grid_setup_kernel<<<B, 1024, 0, st>>>(R, M, w.ncell_max, GRID_H_SCALE, w.hdr);
     DVM_LAUNCH_CHECK();
     DVM_CUDA(cudaMemsetAsync(w.start, 0, (size_t)B * w.stride * sizeof(int), st));
     DVM_CUDA(cudaMemsetAsync(w.cstart, 0, (size_t)B * (GRID_COARSE_MAX + 1) * sizeof(int), st));

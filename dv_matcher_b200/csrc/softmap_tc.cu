@@ -634,7 +634,6 @@ static int make_operand_map(CUtensorMap* map, const uint16_t* base, bool bf16, i
 }
 
 static int choose_split(int B, int N, int M) {
-    if (const char* e = getenv("DVM_TC_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= TC_MAX_SPLIT) return v; }   // experiments only
     const int row_blocks = ceil_div(N, TC_BM);
     const int tiles = ceil_div(M, TC_BN);
     int best = 1; double best_eff = -1.0;

@@ -43,11 +43,11 @@ def match_deform(feat1, feat2, verts1, verts2, graphs, deformer, alpha=100.0, k_
 
     Returns a dict of device tensors; nothing is synchronised or copied to the host here."""
     B, N, _ = verts1.shape
-    sm, vt = match(feat1, feat2, verts1, verts2, alpha, prec)              # [2B,...]: rows 0..B-1 = 1->2, B..2B-1 = 2->1
     src = torch.cat([verts1, verts2])                                      # source cloud of each of the 2B problems
     tgt = torch.cat([verts2, verts1])
     fsrc = torch.cat([feat1, feat2])
     ftgt = torch.cat([feat2, feat1])
+    sm, vt = maps.soft_map(fsrc, ftgt, alpha, v=tgt, prec=prec)            # [2B,...]: rows 0..B-1 = 1->2, B..2B-1 = 2->1
     idx_self = ops.knn3(src, src, k_deform)                                # idx11 | idx22  (models/loss.py:1229-1230)
     idx_tgt = torch.cat([idx_self[B:], idx_self[:B]])
     fps = graphs.nodes_idx
