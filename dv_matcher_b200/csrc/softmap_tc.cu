@@ -38,7 +38,8 @@ constexpr int TC_BLK_BYTES = 128 * 128;        // one 128-row x 64-element K blo
 constexpr int TC_EXT_BYTES = 128 * 32;         // one 128-row x 16-element K block
 constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_CHUNK = 16;               // columns per min-tree
-constexpr int TC_PRIME_STRIDE = 16;        // priming pass: every 16th tile
+constexpr int TC_PRIME_STRIDE = 10;        // priming pass: every 10th tile.  Measured at 4 x 50k x 50k (prime + sweep, ms): stride 16: 3.24,
+                                           // 12: 3.18, 10: 3.155, 8: 3.15; <= 6: thresholds so tight that rows run out of candidates (slow path)
 constexpr int TC_PRIME_MIN_TILES = 128;
 constexpr int TC_PREP_ROWS = 32;           // rows per block of the operand preparation (8 warps x 4 rows)     // ... when the sweep has at least this many tiles (M >= 16k)
 
@@ -173,7 +174,7 @@ struct TcParams {
 // sequence word per slot; producers reserve slots with one warp-aggregated atomicAdd and wait for space, the
 // consumer never waits for a producer, so the protocol cannot deadlock.
 //
-// The list threshold of a row starts from the PRIMING pass (8th smallest key of a 1/16 column sample ~ rank 130) and
+// The list threshold of a row starts from the PRIMING pass (8th smallest chunk minimum of a 1/10 column sample ~ rank 80) and
 // is shared between column-split CTAs via atomicMin in global memory.  Whatever the thresholds were, every column a
 // list discarded has key >= the list's final threshold, which finalize receives as the discard bound `t`.
 // Keys live in the half domain  key = (d~^2 - |x~|^2) / 2.
@@ -745,7 +746,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     }
     if (smem > 227 * 1024) { set_error("launch_cand_tc: C=%d needs %zu bytes of shared memory", C, smem); return DVM_ERR_UNSUPPORTED; }
     prof_begin(st);
-    if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 16th tile (6 % of the sweep's MMA work)
+    if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 10th tile (10 % of the sweep's MMA work)
         TcParams pp = p;
         pp.tile_stride = TC_PRIME_STRIDE; pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
         dim3 gridp(ceil_div(N, TC_BM), 1, B);
