@@ -7,13 +7,15 @@
 // fp32 rounding an SGEMM commits anyway -- so the layer stays inside the 1e-4 bound on deformed coordinates with two
 // orders of magnitude to spare, at 1/3 of the TF32 tensor rate instead of the SIMT fp32 rate.
 //
-// Per CTA: 128 rows of x (UMMA M = 128) against BN <= 256 output features (UMMA N = BN), K streamed in blocks of
-// 16 fp32 (64-byte swizzle rows) through a 2-stage TMA ring.  Stage layout: [x hi | W hi | x lo | W lo]; TMA writes
-// the raw fp32 into the hi half, four converter warps split it in place (hi) and into the lo half, then hand the stage
-// to the MMA issuer (fence.proxy.async + mbarrier).  Two CTAs are resident per SM (2 x 99 KB shared memory, 2 x 256 TMEM
-// columns), so the epilogue of one (TMEM -> bias -> ELU -> global) overlaps the K loop of the other.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = converters, then
-// epilogue of the low column half, warps 6..9 = epilogue of the high column half (TMEM lane quarter = warp % 4).
+// Persistent kernel: one CTA per SM walks the tiles (128 rows of x = UMMA M, BN <= 256 output features = UMMA N; the
+// N tiles of a row block are neighbours in the walk, so x is read from DRAM once).  K streams in blocks of 16 fp32
+// (64-byte swizzle rows) through a 4-stage TMA ring that runs across tile boundaries.  Stage layout
+// [x hi | W hi | x lo | W lo]: TMA writes the raw fp32 into the hi half, four converter warps split it in place (hi)
+// and into the lo half and hand the stage to the MMA issuer (fence.proxy.async + mbarrier).  The accumulator is
+// double-buffered in TMEM (2 x BN columns): eight epilogue warps (TMEM -> bias -> ELU -> global) drain tile i while
+// the MMAs of tile i+1 run.
+// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = converters,
+// warps 6..13 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 6) / 4).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -21,8 +23,8 @@ namespace dvm {
 
 constexpr int LIN_BM = 128;
 constexpr int LIN_BK = 16;                 // fp32 per K block = one 64-byte swizzle row
-constexpr int LIN_NST = 2;
-constexpr int LIN_THREADS = 320;
+constexpr int LIN_NST = 4;
+constexpr int LIN_THREADS = 448;
 constexpr int LIN_ROW_BYTES = LIN_BK * 4;
 
 // K-major SWIZZLE_64B operand descriptor: rows of 64 B, 8-row atoms 512 B apart
@@ -45,6 +47,7 @@ __device__ __forceinline__ float tf32_rn(float v) {
 
 struct LinParams {
     int rows, K, N, BN;
+    int n_tiles, tiles_total;      // N tiles per row block, all tiles
     int out_pitch, act;            // act: 0 = identity, 1 = ELU(alpha = 1)
     uint32_t idesc, tmem_cols;
     const float* bias;             // [N] or nullptr
@@ -52,28 +55,28 @@ struct LinParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(LIN_THREADS, 2)
+__global__ void __launch_bounds__(LIN_THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const LinParams p) {
     extern __shared__ uint8_t lin_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lin_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.y * LIN_BM;          // N tiles of one row block are neighbours in launch order: x is read from DRAM once
-    const int n0 = blockIdx.x * BN;
     const int KB = (p.K + LIN_BK - 1) / LIN_BK;
     constexpr uint32_t half_bytes = (uint32_t)(LIN_BM + BN) * LIN_ROW_BYTES;      // hi (or lo) part of one stage
     constexpr uint32_t stage_bytes = 2 * half_bytes;
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;                                   // TMEM columns per accumulator stage
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LIN_NST * stage_bytes);
-    uint64_t* full = bars;                  // TMA -> converters
-    uint64_t* conv = bars + LIN_NST;        // converters -> MMA
-    uint64_t* empty = bars + 2 * LIN_NST;   // MMA -> TMA
-    uint64_t* accum = bars + 3 * LIN_NST;   // MMA -> epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * LIN_NST + 1);
-    float* bias_s = reinterpret_cast<float*>(bars + 3 * LIN_NST + 2);          // [BN]
-    for (int i = threadIdx.x; i < BN; i += LIN_THREADS) bias_s[i] = (p.bias != nullptr && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+    uint64_t* full = bars;                  // [NST] TMA -> converters
+    uint64_t* conv = bars + LIN_NST;        // [NST] converters -> MMA
+    uint64_t* empty = bars + 2 * LIN_NST;   // [NST] MMA -> TMA
+    uint64_t* tfull = bars + 3 * LIN_NST;   // [2]   MMA -> epilogue
+    uint64_t* tempty = tfull + 2;           // [2]   epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_s = reinterpret_cast<float*>(tempty + 4);                         // [n_tiles * BN]
+    for (int i = threadIdx.x; i < p.n_tiles * BN; i += LIN_THREADS) bias_s[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LIN_NST; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
-        mbar_init(accum, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
@@ -89,43 +92,55 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % LIN_NST;
-                mbar_wait(&empty[s], ((kb / LIN_NST) & 1) ^ 1);
-                uint8_t* st = smem + s * stage_bytes;
-                mbar_arrive_expect_tx(&full[s], half_bytes);
-                tma_load_3d(&tmX, &full[s], st, kb * LIN_BK, row0, 0);
-                tma_load_3d(&tmW, &full[s], st + LIN_BM * LIN_ROW_BYTES, kb * LIN_BK, n0, 0);
+            int g = 0;                                                            // running K-block counter: ring slot and phase
+            for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+                const int row0 = (tile / p.n_tiles) * LIN_BM, n0 = (tile % p.n_tiles) * BN;
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const int s = g % LIN_NST;
+                    mbar_wait(&empty[s], ((g / LIN_NST) & 1) ^ 1);
+                    uint8_t* st = smem + s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], half_bytes);
+                    tma_load_3d(&tmX, &full[s], st, kb * LIN_BK, row0, 0);
+                    tma_load_3d(&tmW, &full[s], st + LIN_BM * LIN_ROW_BYTES, kb * LIN_BK, n0, 0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % LIN_NST;
-                mbar_wait(&conv[s], (kb / LIN_NST) & 1);
+            int g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);                     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t xa = smem_u32(smem + s * stage_bytes);
-                const uint32_t wa = xa + LIN_BM * LIN_ROW_BYTES;
+                const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const int s = g % LIN_NST;
+                    mbar_wait(&conv[s], (g / LIN_NST) & 1);
+                    tc_fence_after();
+                    const uint32_t xa = smem_u32(smem + s * stage_bytes);
+                    const uint32_t wa = xa + LIN_BM * LIN_ROW_BYTES;
 #pragma unroll
-                for (int k = 0; k < LIN_BK / 8; ++k) {
-                    const uint64_t xh = umma_desc_sw64(xa + k * 32), wh = umma_desc_sw64(wa + k * 32);
-                    const uint64_t xl = umma_desc_sw64(xa + half_bytes + k * 32), wl = umma_desc_sw64(wa + half_bytes + k * 32);
-                    tc_mma_tf32(tmem_base, xl, wh, p.idesc, (kb | k) != 0);
-                    tc_mma_tf32(tmem_base, xh, wl, p.idesc, 1u);
-                    tc_mma_tf32(tmem_base, xh, wh, p.idesc, 1u);
+                    for (int k = 0; k < LIN_BK / 8; ++k) {
+                        const uint64_t xh = umma_desc_sw64(xa + k * 32), wh = umma_desc_sw64(wa + k * 32);
+                        const uint64_t xl = umma_desc_sw64(xa + half_bytes + k * 32), wl = umma_desc_sw64(wa + half_bytes + k * 32);
+                        tc_mma_tf32(d, xl, wh, p.idesc, (kb | k) != 0);
+                        tc_mma_tf32(d, xh, wl, p.idesc, 1u);
+                        tc_mma_tf32(d, xh, wh, p.idesc, 1u);
+                    }
+                    tc_commit(&empty[s]);
                 }
-                tc_commit(&empty[s]);
+                tc_commit(&tfull[acc]);
             }
-            tc_commit(accum);
         }
-    } else {
-        if (warp < 6) {
-            const int t = threadIdx.x - 64;                       // 0..127
-            constexpr int n_vec = (int)(half_bytes >> 4);
-            constexpr int n_it = (n_vec + 127) / 128;
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % LIN_NST;
-                mbar_wait(&full[s], (kb / LIN_NST) & 1);
+    } else if (warp < 6) {
+        const int t = threadIdx.x - 64;                       // 0..127
+        constexpr int n_vec = (int)(half_bytes >> 4);
+        constexpr int n_it = (n_vec + 127) / 128;
+        int g = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const int s = g % LIN_NST;
+                mbar_wait(&full[s], (g / LIN_NST) & 1);
                 float4* hi = reinterpret_cast<float4*>(smem + s * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(smem + s * stage_bytes + half_bytes);
                 float4 v[n_it];
@@ -144,45 +159,56 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 if (lane == 0) mbar_arrive(&conv[s]);
             }
         }
+    } else {
         // ---- epilogue: a warp owns TMEM lanes (warp % 4) * 32 .. + 31 = rows of the block, and one column half
-        mbar_wait_backoff(accum, 0);
-        tc_fence_after();
         const int q = warp & 3;
-        const int row = row0 + q * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* orow = p.out + (size_t)row * p.out_pitch;
-        const bool vec_ok = (p.out_pitch & 3) == 0;
+        const int hf = (warp - 6) >> 2;
         constexpr int CH = BN >= 32 ? BN / 2 : BN;                 // columns per epilogue warp
-        const int cbeg = (warp >= 6 && BN >= 32) ? CH : 0;
-        if (warp < 6 || BN >= 32) {
-            float v[2][16];
-            tc_ld16_issue(taddr + cbeg, v[0]);
+        const bool has_cols = BN >= 32 || hf == 0;
+        const int cbeg = (BN >= 32) ? hf * CH : 0;
+        const bool vec_ok = (p.out_pitch & 3) == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int row0 = (tile / p.n_tiles) * LIN_BM, n0 = (tile % p.n_tiles) * BN;
+            mbar_wait_backoff(&tfull[acc], (it >> 1) & 1);
+            tc_fence_after();
+            if (has_cols) {
+                const int row = row0 + q * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+                float* orow = p.out + (size_t)row * p.out_pitch;
+                float v[2][16];
+                tc_ld16_issue(taddr + cbeg, v[0]);
 #pragma unroll
-            for (int ci = 0; ci < CH / 16; ++ci) {
-                const int c0 = cbeg + ci * 16;
-                float (&cur)[16] = v[ci & 1];
-                tc_ld16_wait(cur);
-                if (ci + 1 < CH / 16) tc_ld16_issue(taddr + c0 + 16, v[(ci + 1) & 1]);
-                const int n = n0 + c0;
+                for (int ci = 0; ci < CH / 16; ++ci) {
+                    const int c0 = cbeg + ci * 16;
+                    float (&cur)[16] = v[ci & 1];
+                    tc_ld16_wait(cur);
+                    if (ci + 1 < CH / 16) tc_ld16_issue(taddr + c0 + 16, v[(ci + 1) & 1]);
+                    const int n = n0 + c0;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
-                    cur[j] += b4.x; cur[j + 1] += b4.y; cur[j + 2] += b4.z; cur[j + 3] += b4.w;
-                }
-                if (p.act == 1) {
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + j);
+                        cur[j] += b4.x; cur[j + 1] += b4.y; cur[j + 2] += b4.z; cur[j + 3] += b4.w;
+                    }
+                    if (p.act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) cur[j] = cur[j] > 0.f ? cur[j] : expf(cur[j]) - 1.f;     // torch's CUDA ELU formula
-                }
-                if (row < p.rows) {
-                    if (vec_ok && n + 16 <= p.N) {
+                        for (int j = 0; j < 16; ++j) cur[j] = cur[j] > 0.f ? cur[j] : expf(cur[j]) - 1.f;     // torch's CUDA ELU formula
+                    }
+                    if (row < p.rows) {
+                        if (vec_ok && n + 16 <= p.N) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow + n + j) = make_float4(cur[j], cur[j + 1], cur[j + 2], cur[j + 3]);
-                    } else {
+                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow + n + j) = make_float4(cur[j], cur[j + 1], cur[j + 2], cur[j + 3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (n + j < p.N) orow[n + j] = cur[j];
+                            for (int j = 0; j < 16; ++j) if (n + j < p.N) orow[n + j] = cur[j];
+                        }
                     }
                 }
             }
+            tc_fence_before();                                 // this warp's TMEM reads are complete (wait::ld above)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
         }
     }
     tc_fence_before();
@@ -225,24 +251,28 @@ extern "C" int dvm_linear_act_fwd(const float* x, long long rows, int K, int x_p
     p.rows = (int)rows; p.K = K; p.N = N;
     p.BN = N >= 256 ? 256 : N > 64 ? 128 : N > 16 ? 64 : 16;
     p.out_pitch = out_pitch; p.act = act; p.bias = bias; p.out = out;
-    p.tmem_cols = 32; while ((int)p.tmem_cols < p.BN) p.tmem_cols *= 2;
+    p.n_tiles = ceil_div(N, p.BN);
+    const long long tiles = (long long)p.n_tiles * ceil_div((int)rows, LIN_BM);
+    if (tiles >= (1ll << 31)) { set_error("dvm_linear_act_fwd: rows=%lld too large", rows); return DVM_ERR_INVALID_ARG; }
+    p.tiles_total = (int)tiles;
+    p.tmem_cols = 32; while ((int)p.tmem_cols < 2 * (p.BN < 32 ? 32 : p.BN)) p.tmem_cols *= 2;      // two accumulator stages
     // instruction descriptor: D = f32 (bits 4-5 = 1), A/B = tf32 (2) at bits 7-9 / 10-12, K-major, N >> 3 at 17-22, M >> 4 at 24-28
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(LIN_BM >> 4) << 24);
     CUtensorMap tmX, tmW;
     int rc;
     if ((rc = make_f32_map(&tmX, x, rows, K, x_pitch, LIN_BM))) return rc;
     if ((rc = make_f32_map(&tmW, W, N, K, w_pitch, p.BN))) return rc;
-    const size_t smem = (size_t)LIN_NST * 2 * (LIN_BM + p.BN) * LIN_ROW_BYTES + 1024 + 128 + (size_t)p.BN * 4;
+    const size_t smem = (size_t)LIN_NST * 2 * (LIN_BM + p.BN) * LIN_ROW_BYTES + 1024 + 256 + (size_t)p.n_tiles * p.BN * 4;
+    if (smem > 227 * 1024) { set_error("dvm_linear_act_fwd: N=%d needs %zu bytes of shared memory", N, smem); return DVM_ERR_UNSUPPORTED; }
     static bool attr_done = false;
     if (!attr_done) {
-        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    dim3 grid(ceil_div(N, p.BN), ceil_div((int)rows, LIN_BM));
-    if (grid.y > 65535) { set_error("dvm_linear_act_fwd: rows=%lld too large", rows); return DVM_ERR_INVALID_ARG; }
+    const int grid = p.tiles_total < kNumSM ? p.tiles_total : kNumSM;          // persistent: one CTA per SM
     switch (p.BN) {
         case 256: linear_tf32x3_kernel<256><<<grid, LIN_THREADS, smem, st>>>(tmX, tmW, p); break;
         case 128: linear_tf32x3_kernel<128><<<grid, LIN_THREADS, smem, st>>>(tmX, tmW, p); break;

@@ -59,8 +59,9 @@ def dist_loss_term(feat, dist, n_sample, k, numbers=None):
     rn = torch.as_tensor(numbers, device=feat.device, dtype=torch.long)
     f1 = feat[:, rn]                                               # [B,S,C]
     idx = knn(f1, feat, k)                                         # [B,S,k]
-    f2 = index_points(feat, idx)                                   # [B,S,k,C]
-    dist_result = torch.norm(f2 - f1[:, :, None, :], dim=-1)       # [B,S,k]
+    # ||feat[idx] - f1||: the reference gathers f2 = index_points(feat, idx) ([B,S,k,C], 256 MB per shape at S=1000,
+    # k=500) and takes the norm; the same direct-difference distances are a gather from the [B,S,N] distance matrix
+    dist_result = torch.gather(torch.cdist(f1, feat, compute_mode="donot_use_mm_for_euclid_dist"), 2, idx)   # [B,S,k]
     # dist[i, idx[i], idx_num[i]]: one batched gather instead of the reference's Python loop over B
     bidx = torch.arange(B, device=feat.device)[:, None, None]
     dist_f = dist[bidx, idx, rn[None, :, None]].float()            # torch.zeros_like(idx, dtype=float) in the reference

@@ -654,3 +654,32 @@ def test_deformer_decoder_tensor_core_path_matches_torch_mlp():
     scale = want64.abs().max().item()
     assert (got.double() - want64).abs().max().item() / scale < 2e-5
     assert (got - want).abs().max().item() / scale < 2e-5
+
+
+def test_geodesic_error_evaluator_matches_bruteforce():
+    """eval/main.m:27-38 restated in numpy (knnsearch = exact NN, lowest index on ties; lookup M_T(idx, vts_tar))."""
+    from dv_matcher_b200 import evalio
+    g = np.random.default_rng(5)
+    S, N, C, L = 3, 700, 64, 200
+    phis = [g.standard_normal((N + 10 * i, C)).astype(np.float32) for i in range(S)]
+    vts = [g.integers(1, N + 1, size=L) for _ in range(S)]
+    Ms = []
+    for i in range(S):
+        p = g.standard_normal((N + 10 * i, 3))
+        Ms.append(np.sqrt(((p[:, None] - p[None]) ** 2).sum(-1)))
+    arr, errs, avg = evalio.evaluate_pairs(phis, vts, Ms)
+    want = np.zeros((S, S))
+    all_e = []
+    for tar in range(S):
+        for src in range(S):
+            if src == tar:
+                continue
+            q = phis[src][vts[src] - 1].astype(np.float64)
+            d = ((q[:, None, :] - phis[tar][None].astype(np.float64)) ** 2).sum(-1)
+            idx = d.argmin(1)
+            e = Ms[tar][idx, vts[tar] - 1]
+            want[src, tar] = e.mean()
+            all_e.append(e)
+    assert np.allclose(arr, want, rtol=0, atol=1e-12)
+    assert np.array_equal(errs, np.concatenate(all_e))
+    assert abs(avg - want[~np.eye(S, dtype=bool)].mean()) < 1e-12

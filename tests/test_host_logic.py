@@ -5,6 +5,7 @@ import sys
 import types
 
 import pytest
+import numpy as np
 import torch
 import torch.multiprocessing as mp
 
@@ -102,3 +103,43 @@ def test_sparse_soft_map_protocol_cpu():
     vals, idx = torch.topk(a, 3, dim=-1)
     assert torch.equal(dense, torch.zeros_like(a).scatter(-1, idx, vals))
     assert torch.equal(sm.transpose(1, 2), dense.transpose(1, 2)) and sm.dim() == 3 and sm.size(2) == 12
+
+
+# ------------------------------------------------------------------------------------------------
+# wire / on-disk formats (row f4)
+# ------------------------------------------------------------------------------------------------
+def test_map_txt_and_feature_mat_formats_match_the_reference_writers(tmp_path):
+    """Same bytes as test.py:111-133 (np.savetxt fmt '%i' of the 1-based [N,1] map; savemat key 'uphi')."""
+    import scipy.io
+    from dv_matcher_b200 import evalio
+    g = np.random.default_rng(0)
+    t12 = torch.from_numpy(g.integers(1, 500, size=(1, 500, 1)))
+    t21 = torch.from_numpy(g.integers(1, 500, size=(1, 480, 1)))
+    p12, p21 = evalio.save_maps_txt(str(tmp_path), "mesh052", "mesh053", t12, t21)
+    assert p12.endswith("T/T_mesh052_mesh053.txt") and p21.endswith("T/T_mesh053_mesh052.txt")
+    ref = tmp_path / "ref.txt"
+    np.savetxt(ref, t12.detach().cpu().squeeze(0).numpy(), fmt="%i")            # the reference's own three lines
+    assert open(p12, "rb").read() == open(ref, "rb").read()
+    assert np.array_equal(evalio.load_map_txt(p21), t21.reshape(-1).numpy())
+    feat = torch.randn(1, 500, 128)
+    pf = evalio.save_features_mat(str(tmp_path), "mesh052", feat)
+    assert pf.endswith("feature/usefeature_mesh052.mat")
+    m = scipy.io.loadmat(pf)
+    assert m["uphi"].shape == (500, 128) and np.array_equal(m["uphi"], feat[0].numpy())
+    assert np.array_equal(evalio.load_features_mat(pf), feat[0].numpy())
+
+
+def test_off_vts_and_cache_round_trip(tmp_path):
+    from dv_matcher_b200 import evalio
+    pts = np.random.default_rng(1).standard_normal((37, 3)).astype(np.float32)
+    p = tmp_path / "a.off"
+    evalio.save_off_file(str(p), pts)
+    lines = open(p).read().split("\n")
+    assert lines[0] == "OFF" and lines[1] == "37 0 0" and lines[2] == f"{pts[0][0]} {pts[0][1]} {pts[0][2]}"    # deform.py:79-84
+    assert np.allclose(evalio.load_off_vertices(str(p)), pts, rtol=0, atol=1e-6)
+    (tmp_path / "m.vts").write_text("3\n1\n37\n")
+    assert evalio.load_vts(str(tmp_path / "m.vts")).tolist() == [3, 1, 37]
+    c = tmp_path / "cache.pt"
+    evalio.save_cache(str(c), [torch.from_numpy(pts)], ["a"], [torch.arange(5)], [torch.zeros(37, 37, dtype=torch.float64)])
+    v, names, fps, dist = evalio.load_cache(str(c))
+    assert names == ["a"] and torch.equal(v[0], torch.from_numpy(pts)) and fps[0].tolist() == [0, 1, 2, 3, 4] and dist[0].dtype == torch.float64
