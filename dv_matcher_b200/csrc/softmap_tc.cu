@@ -25,22 +25,22 @@
 
 namespace dvm {
 
-constexpr int TC_SUB = 128;           // rows per UMMA (M)
-constexpr int TC_BM = 2 * TC_SUB;     // rows per CTA
-constexpr int TC_BN = 128;            // columns per tile (UMMA N)
+constexpr int TC_SUB = 128;           // rows per CTA (its half of the UMMA M = 256 of the CTA pair)
+constexpr int TC_BM = 2 * TC_SUB;     // rows per CTA PAIR (cluster of 2, tcgen05 cta_group::2)
+constexpr int TC_BN = 256;            // columns per tile (UMMA N); each CTA of the pair stages 128 of them
 constexpr int TC_KBLK = 64;           // 16-bit elements per 128-byte swizzle row
 constexpr int TC_KEXT = 16;           // extra K block: norm columns (one UMMA K step), 32-byte swizzle rows
 constexpr int TC_SCAN_WARPS = 16;      // epilogue scanners
-constexpr int TC_CONS_WARPS = 8;       // epilogue consumers (one per 32 rows: sub-block x TMEM lane quarter)
+constexpr int TC_CONS_WARPS = 8;       // epilogue consumers (one per 32 rows x column half of the tile)
 constexpr int TC_THREADS = 64 + 32 * (TC_SCAN_WARPS + TC_CONS_WARPS);
-constexpr int TC_NST = 2;             // Y ring depth
+constexpr int TC_NST = 3;             // Y ring depth
 constexpr int TC_BLK_BYTES = 128 * 128;        // one 128-row x 64-element K block
 constexpr int TC_EXT_BYTES = 128 * 32;         // one 128-row x 16-element K block
 constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_CHUNK = 16;               // columns per min-tree
 constexpr int TC_PRIME_STRIDE = 10;        // priming pass: every 10th tile.  Measured at 4 x 50k x 50k (prime + sweep, ms): stride 16: 3.24,
                                            // 12: 3.18, 10: 3.155, 8: 3.15; <= 6: thresholds so tight that rows run out of candidates (slow path)
-constexpr int TC_PRIME_MIN_TILES = 128;
+constexpr int TC_PRIME_MIN_TILES = 64; 
 constexpr int TC_PREP_ROWS = 32;           // rows per block of the operand preparation (8 warps x 4 rows)     // ... when the sweep has at least this many tiles (M >= 16k)
 
 
@@ -256,15 +256,16 @@ __device__ __forceinline__ void prime_chunk(const float (&k)[TC_CHUNK], float (&
 
 // kPrime: priming pass -- strided tile sample, hard mode, only outputs are thr_global / rmin_global.
 template <bool kSoft, bool kPrime>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXe,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYe, const TcParams p) {
     constexpr int K = kPrime ? KP : KC;
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzled operand tiles need 1024-byte alignment (checked below)
     const int unit = p.KB * TC_BLK_BYTES + TC_EXT_BYTES;  // one 128-row operand block, all of K
-    uint8_t* Xs = smem;                                   // [2 sub-blocks][KB x 16 KB | 4 KB]
-    uint8_t* Ys = Xs + 2 * unit;                          // [NST][KB x 16 KB | 4 KB]
+    uint8_t* Xs = smem;                                   // [KB x 16 KB | 4 KB]: this CTA's 128 rows (its half of UMMA M = 256)
+    uint8_t* Ys = Xs + unit;                              // [NST][KB x 16 KB | 4 KB]: this CTA's 128 columns of every tile (half of N)
     uint8_t* q_mem = Ys + TC_NST * unit;                  // [TC_CONS_WARPS][Q_CAP][Q_ENTRY]
+    // lists and row state are indexed by  li = column half * 128 + CTA-local row  (a row has one list per column half of the tile)
     float2* lists = reinterpret_cast<float2*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][LIST_STRIDE] (key, idx)
     float* thr_hi_s = reinterpret_cast<float*>(lists + TC_BM * LIST_STRIDE);           // [256] bound read by the scanners
     float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
@@ -276,18 +277,19 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     float* worst_s = xx_s + TC_BM;                        // [256] largest key of the row's list (slot number in its low bits)
     QCtl* qctl = reinterpret_cast<QCtl*>(worst_s + TC_BM);   // [TC_CONS_WARPS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(qctl + TC_CONS_WARPS);
-    uint64_t* full = bars;                 // [NST]
-    uint64_t* empty = bars + TC_NST;       // [NST]
-    uint64_t* tfull = bars + 2 * TC_NST;   // [2]
-    uint64_t* tempty = tfull + 2;          // [2]
-    uint64_t* xfull = tempty + 2;          // [1]
+    uint64_t* full = bars;                 // [NST]   leader's copy is used: expect_tx covers the TMA of BOTH CTAs
+    uint64_t* empty = bars + TC_NST;       // [NST]   per CTA, signalled by the leader's multicast commit
+    uint64_t* tfull = bars + 2 * TC_NST;   // [2]     per CTA, multicast commit
+    uint64_t* tempty = tfull + 2;          // [2]     leader's copy: 2 x 16 scanner warps arrive
+    uint64_t* xfull = tempty + 2;          // [1]     leader's copy
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfull + 1);
 
     const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction: lives in uniform registers
     const int lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();             // 0 = leader (issues the MMAs), 1 = peer
     const int b = blockIdx.z;
     const int split = blockIdx.y;
-    const int row0 = blockIdx.x * TC_BM;
+    const int row0 = (blockIdx.x >> 1) * TC_BM + (int)crank * TC_SUB;   // first row of THIS CTA
     const int tile0 = split * p.tiles_per_split;
     const int span = min(p.tiles_per_split, p.tiles_total - tile0);
     const int ntiles = (span + p.tile_stride - 1) / p.tile_stride;     // tiles tile0 + it * tile_stride
@@ -295,7 +297,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < TC_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, TC_SCAN_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 2 * TC_SCAN_WARPS); }
         mbar_init(xfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmXe);
@@ -306,8 +308,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     for (int e = threadIdx.x; e < TC_CONS_WARPS * Q_CAP; e += TC_THREADS) *reinterpret_cast<unsigned*>(q_mem + e * Q_ENTRY + 72) = 0u;
     for (int e = threadIdx.x; e < TC_BM * LIST_STRIDE; e += TC_THREADS)      // empty slots: LIST_EMPTY with the slot number in the low bits
         lists[e] = make_float2(__uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)((e % LIST_STRIDE) & 15)), __int_as_float(-1));
-    for (int rl = threadIdx.x; rl < TC_BM; rl += TC_THREADS) {
-        const int row = row0 + rl;
+    for (int rl = threadIdx.x; rl < TC_BM; rl += TC_THREADS) {        // rl = li: both column halves start from the same state
+        const int row = row0 + (rl & (TC_SUB - 1));
         float thl = -INFINITY, thm = -INFINITY, kr = INFINITY, r = INFINITY, xx = 0.f;   // padding rows never enqueue
         if (row < p.N) {
             xx = __ldg(p.xx + (size_t)b * p.N + row);
@@ -327,45 +329,44 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
         thr_hi_s[rl] = kSoft ? fmaxf(thl, thm) : thl;
     }
-    if (warp == 1) {                        // TMEM: all 512 columns (2 accumulator stages x 2 sub-blocks x 128)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {                        // TMEM of the pair: 512 columns per CTA (2 accumulator stages x 256), same warp in both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                     // both CTAs' barriers are initialised before anybody signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        // =============================== TMA producer ===============================
+        // =============================== TMA producer (both CTAs) ===============================
         if (lane == 0) {
-            mbar_arrive_expect_tx(xfull, 2 * unit);
-            for (int sb = 0; sb < 2; ++sb) {
-                uint8_t* dst = Xs + sb * unit;
-                for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(&tmX, xfull, dst + kb * TC_BLK_BYTES, kb * TC_KBLK, row0 + sb * TC_SUB, b);
-                tma_load_3d(&tmXe, xfull, dst + p.KB * TC_BLK_BYTES, 0, row0 + sb * TC_SUB, b);
-            }
+            if (crank == 0) mbar_arrive_expect_tx(xfull, 2 * unit);                  // the pair's X rows: 2 x 128
+            for (int kb = 0; kb < p.KB; ++kb) tma_load_3d_pair(&tmX, xfull, Xs + kb * TC_BLK_BYTES, kb * TC_KBLK, row0, b);
+            tma_load_3d_pair(&tmXe, xfull, Xs + p.KB * TC_BLK_BYTES, 0, row0, b);
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_NST;
                 const uint32_t ph = (it / TC_NST) & 1;
-                mbar_wait(empty + s, ph ^ 1);
-                mbar_arrive_expect_tx(full + s, unit);
+                mbar_wait(empty + s, ph ^ 1);                                       // own copy: the leader's commit reaches both CTAs
+                if (crank == 0) mbar_arrive_expect_tx(full + s, 2 * unit);          // both halves of the tile
                 uint8_t* dst = Ys + s * unit;
-                const int col0 = (tile0 + it * p.tile_stride) * TC_BN;
-                for (int kb = 0; kb < p.KB; ++kb) tma_load_3d(&tmY, full + s, dst + kb * TC_BLK_BYTES, kb * TC_KBLK, col0, b);
-                tma_load_3d(&tmYe, full + s, dst + p.KB * TC_BLK_BYTES, 0, col0, b);
+                const int col0 = (tile0 + it * p.tile_stride) * TC_BN + (int)crank * 128;   // this CTA's half of the tile's columns
+                for (int kb = 0; kb < p.KB; ++kb) tma_load_3d_pair(&tmY, full + s, dst + kb * TC_BLK_BYTES, kb * TC_KBLK, col0, b);
+                tma_load_3d_pair(&tmYe, full + s, dst + p.KB * TC_BLK_BYTES, 0, col0, b);
             }
         }
     } else if (warp == 1) {
-        // =============================== MMA issuer ===============================
-        // A single thread issues 18 MMAs per tile; its instruction stream is on the critical path (it was ~20
-        // instructions per MMA with the descriptors rebuilt every time: 2200 clk per tile, the ceiling of the whole
-        // kernel).  Descriptor halves are precomputed; the loop body is two adds + the MMA.
-        if (lane == 0) {
+        // =============================== MMA issuer (leader CTA only) ===============================
+        // One thread of the leader issues 9 tcgen05.mma.cta_group::2 per tile (M = 256 over the pair, N = 256, K = 16
+        // each): every CTA feeds its own 128 rows of A and its own 128 columns of B from shared memory -- 8 KB per
+        // 128 tensor cycles = 64 B/clk, half of what two single-CTA M = 128 x N = 128 chains read (the whole
+        // shared-memory bandwidth of the SM, which limited the single-CTA version).  Descriptor halves are precomputed;
+        // the loop body is two adds + the MMA.
+        if (crank == 0 && lane == 0) {
             constexpr uint32_t HI128 = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
             constexpr uint32_t HI32 = (256u >> 4) | (1u << 14) | (6u << 29);       // SBO 256 B, version 1, SWIZZLE_32B
-            const uint32_t xlo0 = ((smem_u32(Xs) >> 4) & 0x3FFFu) | (1u << 16);
-            const uint32_t xlo1 = ((smem_u32(Xs + unit) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t xlo = ((smem_u32(Xs) >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t ylo_s0 = ((smem_u32(Ys) >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t ystep = (uint32_t)unit >> 4;                            // stage stride in descriptor units
             const uint32_t ext = (uint32_t)(p.KB * TC_BLK_BYTES) >> 4;
@@ -376,45 +377,37 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const uint32_t ph = (it / TC_NST) & 1;
                 const int acc = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(tempty + acc, aph ^ 1);          // scanners have drained this accumulator stage
-                mbar_wait(full + s, ph);                   // Y tile landed
+                mbar_wait(tempty + acc, aph ^ 1);          // the scanners of BOTH CTAs have drained this accumulator stage
+                mbar_wait(full + s, ph);                   // both halves of the Y tile landed
                 tc_fence_after();
                 const uint32_t ylo = ylo_s0 + (uint32_t)s * ystep;
-                const uint32_t d0 = tmem_base + (uint32_t)(acc * 2) * TC_BN, d1 = d0 + TC_BN;
-                // first K block: k = 0 overwrites the accumulators
-                tc_mma_f16_lohi<false>(d0, xlo0, ylo, HI128, idesc);
-                tc_mma_f16_lohi<false>(d1, xlo1, ylo, HI128, idesc);
+                const uint32_t d0 = tmem_base + (uint32_t)acc * TC_BN;
+                tc_mma_f16_lohi_pair<false>(d0, xlo, ylo, HI128, idesc);           // k = 0 overwrites the accumulator
 #pragma unroll
-                for (int k = 1; k < TC_KBLK / 16; ++k) {   // UMMA_K = 16 -> +32 bytes = +2 descriptor units inside the swizzle row
-                    tc_mma_f16_lohi<true>(d0, xlo0 + 2 * k, ylo + 2 * k, HI128, idesc);
-                    tc_mma_f16_lohi<true>(d1, xlo1 + 2 * k, ylo + 2 * k, HI128, idesc);
-                }
+                for (int k = 1; k < TC_KBLK / 16; ++k)     // UMMA_K = 16 -> +32 bytes = +2 descriptor units inside the swizzle row
+                    tc_mma_f16_lohi_pair<true>(d0, xlo + 2 * k, ylo + 2 * k, HI128, idesc);
                 if (p.KB == 2) {
                     constexpr uint32_t kb1 = TC_BLK_BYTES >> 4;
 #pragma unroll
-                    for (int k = 0; k < TC_KBLK / 16; ++k) {
-                        tc_mma_f16_lohi<true>(d0, xlo0 + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
-                        tc_mma_f16_lohi<true>(d1, xlo1 + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
-                    }
+                    for (int k = 0; k < TC_KBLK / 16; ++k)
+                        tc_mma_f16_lohi_pair<true>(d0, xlo + kb1 + 2 * k, ylo + kb1 + 2 * k, HI128, idesc);
                 }
-                tc_mma_f16_lohi<true>(d0, xlo0 + ext, ylo + ext, HI32, idesc);         // norm block
-                tc_mma_f16_lohi<true>(d1, xlo1 + ext, ylo + ext, HI32, idesc);
-                tc_commit(empty + s);                      // smem slot reusable once these MMAs retire
-                tc_commit(tfull + acc);                    // accumulators ready for the scanners
+                tc_mma_f16_lohi_pair<true>(d0, xlo + ext, ylo + ext, HI32, idesc); // norm block
+                tc_commit_pair(empty + s);                 // smem slot reusable (both CTAs) once these MMAs retire
+                tc_commit_pair(tfull + acc);               // accumulators ready for the scanners of both CTAs
             }
         }
     } else if (warp < 2 + TC_SCAN_WARPS) {
         // =============================== scanners ===============================
         const int ew = warp - 2;                           // 0..15
         const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's
-        const int grp = ew >> 2;                           // 0..3
-        const int sb = grp >> 1;                           // row sub-block
-        const int half = grp & 1;                          // columns half*64 .. +63 of each tile
-        const int cq = sb * 4 + quarter;                    // consumer / queue of this warp's rows
-        const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(sb * TC_SUB + quarter * 32 + lane) * 4u;
+        const int cgp = ew >> 2;                           // column group: columns cgp*64 .. +63 of each 256-column tile
+        const int ch = cgp >> 1;                           // column half: the list / consumer this warp feeds
+        const int cq = ch * 4 + quarter;                   // consumer / queue of this warp's (rows, column half)
+        const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 4u;
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cq * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * TC_BN + half * 64;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgp * 64;
         float priv = INFINITY;
         float pl[KP];
 #pragma unroll
@@ -423,10 +416,10 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         for (int it = 0; it < ntiles; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int col0 = (tile0 + it * p.tile_stride) * TC_BN + half * 64;
+            const int col0 = (tile0 + it * p.tile_stride) * TC_BN + cgp * 64;
             mbar_wait_backoff(tfull + acc, aph);
             tc_fence_after();
-            const uint32_t taddr = t_lane + acc * 2 * TC_BN;
+            const uint32_t taddr = t_lane + acc * TC_BN;
             // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
             float ka[TC_CHUNK], kb[TC_CHUNK];
             tc_ld16_issue(taddr, ka);
@@ -442,11 +435,11 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_wait(kb);
             tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + acc);
+            if (lane == 0) mbar_arrive_leader(tempty + acc);
             if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
         }
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
-            float2* L = lists + (sb * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + half * KP;
+            float2* L = lists + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
 #pragma unroll
             for (int t = 0; t < KP; ++t) L[t] = make_float2(pl[t], 0.f);
         }
@@ -461,13 +454,16 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         // mantissa bits, so "the worst entry and where it sits" is one max-tree.  Entry keys get their column offset
         // packed the same way, so "the best not yet handled key and its column" is one min-tree.  (16 ulp of
         // perturbation, covered by the certificate's E2 term; exact distances are recomputed by finalize anyway.)
-        const int cw = warp - (2 + TC_SCAN_WARPS);          // consumer index: (sub-block, quarter)
-        const int rl0 = cw * 32;                             // first CTA-local row served (sub-block * 128 + quarter * 32)
+        const int cw = warp - (2 + TC_SCAN_WARPS);          // consumer index: column half * 4 + quarter
+        const int rl0 = cw * 32;                             // first list index li served (column half * 128 + quarter * 32); `rl` below is li
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cw * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cw * sizeof(QCtl);
         unsigned head = 0;
-        if (kPrime) {                                        // nothing is queued: wait for the two scanner warps of these rows
-            while (lds_u32_acquire(ctl_a + 8) != 2u) __nanosleep(200);
+        if (kPrime) {                                        // nothing is queued: the consumers of column half 0 wait for the four
+            if (cw < 4) {                                    // scanner warps of their rows (two per column half)
+                const uint32_t ctl_b = ctl_a + 4u * (uint32_t)sizeof(QCtl);
+                while (lds_u32_acquire(ctl_a + 8) != 2u || lds_u32_acquire(ctl_b + 8) != 2u) __nanosleep(200);
+            }
         } else
         for (;;) {
             const unsigned g = head + (unsigned)lane;
@@ -508,7 +504,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; r = r_s[rl]; l = l_s[rl];
                     worst = worst_s[rl];
                     if (!kPrime && p.multi_split)
-                        thl = fminf(thl, 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row0 + rl)) - xx));
+                        thl = fminf(thl, 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)))) - xx));
                 }
                 bool changed = false;
                 float prev = -INFINITY;                               // packed keys handled so far are <= prev
@@ -555,7 +551,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = l; worst_s[rl] = worst;
                     *reinterpret_cast<volatile float*>(thr_hi_s + rl) = kSoft ? fmaxf(thl, thm) : thl;
                     if (!kPrime && p.multi_split && changed && worst < LIST_EMPTY)
-                        atomicMin(p.thr_global + (size_t)b * p.N + row0 + rl, __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
+                        atomicMin(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)), __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
                     todo = false;
                 }
                 done_mask = __ballot_sync(kFull, !todo);
@@ -567,24 +563,30 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         // ---- results of the 32 rows of this consumer
         {
             const int rl = rl0 + lane;
-            const int row = row0 + rl;
-            if (row < p.N) {
+            const int row = row0 + (rl & (TC_SUB - 1));
+            if (row < p.N && (!kPrime || cw < 4)) {
                 const float xx = xx_s[rl];
                 const float2* L = lists + rl * LIST_STRIDE;
                 if (kPrime) {
-                    // merge the two sorted lists of chunk minima (column halves): KP-th smallest of the union, and the minimum
-                    int i = 0, j = KP;
+                    // merge the four sorted lists of chunk minima (column groups; two sit in the other half's list slot):
+                    // KP-th smallest of the union, and the minimum
+                    const float2* L2 = L + TC_SUB * LIST_STRIDE;
+                    int i0 = 0, i1 = KP, i2 = 0, i3 = KP;
                     float w = INFINITY;
                     for (int t = 0; t < KP; ++t) {
-                        const float a = i < KP ? L[i].x : INFINITY, c = j < 2 * KP ? L[j].x : INFINITY;
-                        if (a <= c) { w = a; ++i; } else { w = c; ++j; }
+                        const float a0 = i0 < KP ? L[i0].x : INFINITY, a1 = i1 < 2 * KP ? L[i1].x : INFINITY;
+                        const float a2 = i2 < KP ? L2[i2].x : INFINITY, a3 = i3 < 2 * KP ? L2[i3].x : INFINITY;
+                        const float m01 = fminf(a0, a1), m23 = fminf(a2, a3);
+                        w = fminf(m01, m23);
+                        if (m01 <= m23) { if (a0 <= a1) ++i0; else ++i1; } else { if (a2 <= a3) ++i2; else ++i3; }
                     }
-                    const float m = fminf(L[0].x, L[KP].x);
+                    const float m = fminf(fminf(L[0].x, L[KP].x), fminf(L2[0].x, L2[KP].x));
                     if (w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
                     if (m < LIST_EMPTY) atomicMin(p.rmin_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, m, xx), 0.f)));
                 } else {
                     const size_t g_row = (size_t)b * p.N + row;
-                    const size_t base = (g_row * p.cb.P + split) * KC;
+                    const int part = split * 2 + (cw >> 2);                 // partial list index: (column split, column half)
+                    const size_t base = (g_row * p.cb.P + part) * KC;
                     for (int t = 0; t < K; ++t) {
                         const float2 e = L[t];
                         const bool has = e.x < LIST_EMPTY;
@@ -592,10 +594,10 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                         p.cb.idx[base + t] = has ? __float_as_int(e.y) : -1;
                     }
                     const float thl = thr_list_s[rl];
-                    p.cb.l[g_row * p.cb.P + split] = l_s[rl];
-                    p.cb.r[g_row * p.cb.P + split] = r_s[rl];
+                    p.cb.l[g_row * p.cb.P + part] = l_s[rl];
+                    p.cb.r[g_row * p.cb.P + part] = r_s[rl];
                     // discard bound of this list (true domain): everything it dropped has a key >= thr_list
-                    p.cb.t[g_row * p.cb.P + split] = thl >= LIST_EMPTY ? INFINITY : fmaxf(fmaf(2.f, thl, xx), 0.f);
+                    p.cb.t[g_row * p.cb.P + part] = thl >= LIST_EMPTY ? INFINITY : fmaxf(fmaf(2.f, thl, xx), 0.f);
                 }
             }
         }
@@ -603,9 +605,10 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                     // nobody of the pair still signals barriers / reads shared memory of the other
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -642,15 +645,15 @@ static int choose_split(int B, int N, int M) {
         if (s > 1 && tiles / s < 8) break;                       // keep >= 8 tiles per CTA to amortise the X load
         const int tps = ceil_div(tiles, s);
         if ((s - 1) * tps >= tiles) continue;                    // would leave an empty split
-        const long long ctas = (long long)row_blocks * s * B;
-        const double waves = (double)ctas / kNumSM;
+        const long long ctas = (long long)row_blocks * s * B;          // CTA pairs
+        const double waves = (double)ctas / (kNumSM / 2);
         const double eff = waves / ceil(waves) - 0.02 * (s - 1); // prefer fewer partial lists on ties
         if (eff > best_eff) { best_eff = eff; best = s; }
     }
     return best;
 }
 
-int tc_num_partials(int B, int N, int M) { return choose_split(B, N, M); }
+int tc_num_partials(int B, int N, int M) { return 2 * choose_split(B, N, M); }   // (column split) x (column half of the tile)
 
 struct TcWs {
     uint16_t* Xh; uint16_t* Yh; float* xx; float* yy_max; unsigned* thr_g; unsigned* rmin_g;
@@ -713,7 +716,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     TcParams p{};
     p.N = N; p.M = M; p.KB = w.Cpad / TC_KBLK;
     p.tiles_total = ceil_div(M, TC_BN);
-    const int S = cb.P;
+    const int S = cb.P / 2;
     p.tiles_per_split = ceil_div(p.tiles_total, S);
     p.a2 = alpha * kLog2e;
     // softmax window of the 16-bit pass: terms below exp(-cut) of the row maximum are dropped; the dropped mass is
@@ -723,17 +726,17 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     // instruction descriptor: D=f32 (bits 4-5 = 1), A/B format (0 = f16, 1 = bf16) at bits 7-9 / 10-12, K-major A and B,
     // N >> 3 at bits 17-22, M >> 4 at bits 24-28
     const uint32_t fmt = bf16 ? 1u : 0u;
-    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_SUB >> 4) << 24);
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     p.xx = w.xx; p.cb = cb;
     p.thr_global = w.thr_g;
     p.rmin_global = w.rmin_g;
-    p.multi_split = S > 1;
+    p.multi_split = 1;                               // the two column halves of a tile are separate lists that share thresholds
     p.tile_stride = 1;
     fill_u32_kernel<<<ceil_div(2 * B * N, 256), 256, 0, st>>>(w.thr_g, 0x7f800000u, 2 * B * N);    // +inf (memset cannot write it)
     DVM_LAUNCH_CHECK();
 
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
-    const size_t smem = (2 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 8 * TC_BM * sizeof(float)
+    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 8 * TC_BM * sizeof(float)
                         + TC_CONS_WARPS * sizeof(QCtl) + 128;
     auto kern = soft ? softmap_cand_tc_kernel<true, false> : softmap_cand_tc_kernel<false, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
@@ -749,11 +752,11 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 10th tile (10 % of the sweep's MMA work)
         TcParams pp = p;
         pp.tile_stride = TC_PRIME_STRIDE; pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
-        dim3 gridp(ceil_div(N, TC_BM), 1, B);
+        dim3 gridp(2 * ceil_div(N, TC_BM), 1, B);                 // clusters of 2 CTAs along x
         kprime<<<gridp, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, pp);
         DVM_LAUNCH_CHECK();
     }
-    dim3 grid(ceil_div(N, TC_BM), S, B);
+    dim3 grid(2 * ceil_div(N, TC_BM), S, B);
     kern<<<grid, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, p);
     prof_end(st);
     DVM_LAUNCH_CHECK();

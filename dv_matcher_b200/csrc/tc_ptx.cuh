@@ -136,6 +136,42 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
 
+// ---- CTA-pair (cta_group::2) forms.  The pair is a cluster of 2 CTAs; the leader (cluster rank 0) issues the MMAs.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's leader CTA
+// the TMA of either CTA lands in its OWN shared memory but signals the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {        // arrive on the leader CTA's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {            // arrives on `bar` in BOTH CTAs once the MMAs retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool kAccumulate>
+__device__ __forceinline__ void tc_mma_f16_lohi_pair(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc) {
+    if (kAccumulate)
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+}
+
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda)
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
