@@ -179,12 +179,13 @@ struct TcParams {
 // list discarded has key >= the list's final threshold, which finalize receives as the discard bound `t`.
 // Keys live in the half domain  key = (d~^2 - |x~|^2) / 2.
 constexpr int KP = 8;                  // list length of the priming pass
-constexpr int Q_CAP = 64;              // queue slots per consumer
+constexpr int Q_CAP = 64;              // queue slots per consumer: two single-producer rings of Q_SUB slots
+constexpr int Q_SUB = Q_CAP / 2;       // one ring per scanner warp feeding the consumer
 constexpr int Q_ENTRY = 80;            // bytes: 16 keys | row, first column | sequence word, pad
 constexpr int LIST_STRIDE = KC + 1;    // float2 per row (odd stride in 8-byte units: conflict-poor)
 constexpr float LIST_EMPTY = 3.0e38f;  // "no entry" key (finite, so that a slot number can live in its low mantissa bits)
 
-struct QCtl { unsigned tail, head, done, pad; };
+struct QCtl { unsigned head0, head1, done, pad; };   // ring heads (consumer writes), number of finished producers
 
 __device__ __forceinline__ float ex2_approx(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
 __device__ __forceinline__ float key_dist_approx(float key, float xx) {        // 2 ulp: fine for non-candidate terms
@@ -217,8 +218,8 @@ __device__ __forceinline__ float max16(const float (&k)[16]) {
 // without a primed threshold) the thread bounds it itself -- the largest key of any chunk it has seen is >= the row's
 // 16th smallest key -- so the start-up does not flood the queue with every chunk of every row.
 template <bool kPrivBound>
-__device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase, uint32_t thr_hi_a, uint32_t q_a, uint32_t ctl_a,
-                                           int row_in_q, int lane, float& priv, bool first_tile) {
+__device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase, uint32_t thr_hi_a, uint32_t q_a, uint32_t head_a,
+                                           int row_in_q, int lane, float& priv, bool first_tile, unsigned& tail, unsigned& head_seen) {
     float th = lds_f32(thr_hi_a);
     if (kPrivBound) {
         th = fminf(th, priv);
@@ -227,21 +228,24 @@ __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase
     const bool slow = min16(k) < th;
     const unsigned mask = __ballot_sync(kFull, slow);
     if (mask == 0u) return;                                          // warp-uniform
+    // the ring has ONE producer (this warp): the tail is a warp-uniform register, no atomic; the consumer's head is
+    // re-read only when the ring looks full
     const int n = __popc(mask);
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned*>(__cvta_shared_to_generic(ctl_a)), (unsigned)n);   // QCtl::tail
-    base = __shfl_sync(kFull, base, 0);
-    while ((int)(base + (unsigned)n - lds_u32_volatile(ctl_a + 4)) > Q_CAP) __nanosleep(20);     // QCtl::head: wait for space
+    while ((int)(tail + (unsigned)n - head_seen) > Q_SUB) {
+        head_seen = lds_u32_volatile(head_a);
+        if ((int)(tail + (unsigned)n - head_seen) > Q_SUB) __nanosleep(20);
+    }
     if (slow) {
-        const unsigned g = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
-        const uint32_t ea = q_a + (g % Q_CAP) * Q_ENTRY;
+        const unsigned g = tail + (unsigned)__popc(mask & ((1u << lane) - 1u));
+        const uint32_t ea = q_a + (g % Q_SUB) * Q_ENTRY;
         sts_v4(ea, k[0], k[1], k[2], k[3]);
         sts_v4(ea + 16, k[4], k[5], k[6], k[7]);
         sts_v4(ea + 32, k[8], k[9], k[10], k[11]);
         sts_v4(ea + 48, k[12], k[13], k[14], k[15]);
         sts_v2(ea + 64, __int_as_float(row_in_q), __int_as_float(cbase));
-        sts_u32_release(ea + 72, g / Q_CAP + 1u);                    // publishes the entry
+        sts_u32_release(ea + 72, g / Q_SUB + 1u);                    // publishes the entry
     }
+    tail += (unsigned)n;
 }
 
 // priming pass: the scanner thread keeps the KP smallest CHUNK MINIMA it has seen in a sorted register list (a branch-free
@@ -405,8 +409,10 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int ch = cgp >> 1;                           // column half: the list / consumer this warp feeds
         const int cq = ch * 4 + quarter;                   // consumer / queue of this warp's (rows, column half)
         const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 4u;
-        const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cq * Q_CAP * Q_ENTRY;
+        const uint32_t q_a = smem_u32(q_mem) + (uint32_t)(cq * Q_CAP + (cgp & 1) * Q_SUB) * Q_ENTRY;   // this warp's own ring
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
+        const uint32_t head_a = ctl_a + (uint32_t)(cgp & 1) * 4u;
+        unsigned q_tail = 0, q_head_seen = 0;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgp * 64;
         float priv = INFINITY;
         float pl[KP];
@@ -425,18 +431,18 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_issue(taddr, ka);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + TC_CHUNK, kb);
-            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
             tc_ld16_wait(kb);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
-            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
-            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
             tc_ld16_wait(kb);
             tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty + acc);
-            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, ctl_a, lane, lane, priv, it == 0);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
         }
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
             float2* L = lists + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
@@ -458,7 +464,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int rl0 = cw * 32;                             // first list index li served (column half * 128 + quarter * 32); `rl` below is li
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cw * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cw * sizeof(QCtl);
-        unsigned head = 0;
+        unsigned head = 0, head1 = 0;
+        bool saw_done = false;
         if (kPrime) {                                        // nothing is queued: the consumers of column half 0 wait for the four
             if (cw < 4) {                                    // scanner warps of their rows (two per column half)
                 const uint32_t ctl_b = ctl_a + 4u * (uint32_t)sizeof(QCtl);
@@ -466,17 +473,22 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
         } else
         for (;;) {
-            const unsigned g = head + (unsigned)lane;
-            const uint32_t ea = q_a + (g % Q_CAP) * Q_ENTRY;
-            const bool ready = lds_u32_acquire(ea + 72) == g / Q_CAP + 1u;
+            // lanes 0..15 look at ring 0, lanes 16..31 at ring 1: the leading ready entries of each (ring order)
+            const int sub = lane >> 4;
+            const unsigned g = (sub ? head1 : head) + (unsigned)(lane & 15);
+            const uint32_t ea = q_a + (uint32_t)(sub * Q_SUB + (int)(g % Q_SUB)) * Q_ENTRY;
+            const bool ready = lds_u32_acquire(ea + 72) == g / Q_SUB + 1u;
             const unsigned rb = __ballot_sync(kFull, ready);
-            const int n = (rb == kFull) ? 32 : __ffs(~rb) - 1;        // leading ready entries (queue order)
-            if (n == 0) {
-                if (lds_u32_acquire(ctl_a + 8) == 2u && lds_u32_volatile(ctl_a) == head) break;   // 2 scanner warps (column halves) feed a queue
+            const unsigned r0 = rb & 0xffffu, r1 = rb >> 16;
+            const int n0 = (r0 == 0xffffu) ? 16 : __ffs(~r0) - 1;
+            const int n1 = (r1 == 0xffffu) ? 16 : __ffs(~r1) - 1;
+            if (n0 + n1 == 0) {
+                if (saw_done) break;                                   // nothing was published before the producers finished
+                if (lds_u32_acquire(ctl_a + 8) == 2u) { saw_done = true; continue; }   // look once more: entries precede `done`
                 __nanosleep(32);
                 continue;
             }
-            const bool active = lane < n;
+            const bool active = (lane & 15) < (sub ? n1 : n0);
             float k[TC_CHUNK];
             int rl = -1 - lane, cbase = 0;                            // inactive lanes: unique pseudo rows
             if (active) {
@@ -556,9 +568,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 }
                 done_mask = __ballot_sync(kFull, !todo);
             }
-            head += (unsigned)n;
+            head += (unsigned)n0; head1 += (unsigned)n1;
             __syncwarp();
-            if (lane == 0) sts_u32_release(ctl_a + 4, head);          // QCtl::head: frees the slots
+            if (lane == 0) { sts_u32_release(ctl_a, head); sts_u32_release(ctl_a + 4, head1); }    // QCtl::head0/1: frees the slots
         }
         // ---- results of the 32 rows of this consumer
         {
