@@ -185,7 +185,8 @@ constexpr int Q_ENTRY = 80;            // bytes: 16 keys | row, first column | s
 constexpr int LIST_STRIDE = KC + 1;    // float2 per row (odd stride in 8-byte units: conflict-poor)
 constexpr float LIST_EMPTY = 3.0e38f;  // "no entry" key (finite, so that a slot number can live in its low mantissa bits)
 
-struct QCtl { unsigned head0, head1, done, pad; };   // ring heads (consumer writes), number of finished producers
+struct QCtl { unsigned head0, head1, tail0, tail1, done, pad0, pad1, pad2; };   // ring heads (consumer writes), published tails
+                                                                                // (producers write), number of finished producers
 
 __device__ __forceinline__ float ex2_approx(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
 __device__ __forceinline__ float key_dist_approx(float key, float xx) {        // 2 ulp: fine for non-candidate terms
@@ -217,9 +218,16 @@ __device__ __forceinline__ float max16(const float (&k)[16]) {
 // kPrivBound (hard mode): while the consumer has not published a list threshold yet (first tile of a CTA that starts
 // without a primed threshold) the thread bounds it itself -- the largest key of any chunk it has seen is >= the row's
 // 16th smallest key -- so the start-up does not flood the queue with every chunk of every row.
+// makes the ring entries written so far by all lanes of the warp visible to the consumer: tail word at `tail_a`
+__device__ __forceinline__ void ring_publish(uint32_t tail_a, unsigned tail, int lane) {
+    __syncwarp();                                                    // orders the lanes' entry stores before lane 0's release
+    if (lane == 0) sts_u32_release(tail_a, tail);
+}
+
 template <bool kPrivBound>
 __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase, uint32_t thr_hi_a, uint32_t q_a, uint32_t head_a,
-                                           int row_in_q, int lane, float& priv, bool first_tile, unsigned& tail, unsigned& head_seen) {
+                                           int row_in_q, int lane, float& priv, bool first_tile, unsigned& tail, unsigned& head_seen,
+                                           unsigned& pub) {
     float th = lds_f32(thr_hi_a);
     if (kPrivBound) {
         th = fminf(th, priv);
@@ -229,9 +237,11 @@ __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase
     const unsigned mask = __ballot_sync(kFull, slow);
     if (mask == 0u) return;                                          // warp-uniform
     // the ring has ONE producer (this warp): the tail is a warp-uniform register, no atomic; the consumer's head is
-    // re-read only when the ring looks full
+    // re-read only when the ring looks full.  Entries are PUBLISHED (one fence + the tail word) once per tile, at a
+    // point where the warp has nothing in flight -- a release per entry drained the TMEM-load pipeline every time.
     const int n = __popc(mask);
     while ((int)(tail + (unsigned)n - head_seen) > Q_SUB) {
+        if (pub != tail) { ring_publish(head_a + 8, tail, lane); pub = tail; }     // the consumer must see what it has to free
         head_seen = lds_u32_volatile(head_a);
         if ((int)(tail + (unsigned)n - head_seen) > Q_SUB) __nanosleep(20);
     }
@@ -243,7 +253,6 @@ __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase
         sts_v4(ea + 32, k[8], k[9], k[10], k[11]);
         sts_v4(ea + 48, k[12], k[13], k[14], k[15]);
         sts_v2(ea + 64, __int_as_float(row_in_q), __int_as_float(cbase));
-        sts_u32_release(ea + 72, g / Q_SUB + 1u);                    // publishes the entry
     }
     tail += (unsigned)n;
 }
@@ -306,7 +315,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmXe);
         tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmYe);
-        for (int c = 0; c < TC_CONS_WARPS; ++c) qctl[c] = QCtl{0u, 0u, 0u, 0u};
+        for (int c = 0; c < TC_CONS_WARPS; ++c) qctl[c] = QCtl{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     }
     // row state, lists and queue sequence words (all threads)
     for (int e = threadIdx.x; e < TC_CONS_WARPS * Q_CAP; e += TC_THREADS) *reinterpret_cast<unsigned*>(q_mem + e * Q_ENTRY + 72) = 0u;
@@ -412,7 +421,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)(cq * Q_CAP + (cgp & 1) * Q_SUB) * Q_ENTRY;   // this warp's own ring
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
         const uint32_t head_a = ctl_a + (uint32_t)(cgp & 1) * 4u;
-        unsigned q_tail = 0, q_head_seen = 0;
+        unsigned q_tail = 0, q_head_seen = 0, q_pub = 0;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgp * 64;
         float priv = INFINITY;
         float pl[KP];
@@ -431,18 +440,19 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_issue(taddr, ka);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + TC_CHUNK, kb);
-            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
             tc_ld16_wait(kb);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
-            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
             tc_ld16_wait(ka);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
-            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
             tc_ld16_wait(kb);
             tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty + acc);
-            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
+            if (q_pub != q_tail) { ring_publish(head_a + 8, q_tail, lane); q_pub = q_tail; }     // once per tile
         }
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
             float2* L = lists + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
@@ -452,7 +462,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
-            atomicAdd(reinterpret_cast<unsigned*>(__cvta_shared_to_generic(ctl_a + 8)), 1u);      // QCtl::done
+            atomicAdd(reinterpret_cast<unsigned*>(__cvta_shared_to_generic(ctl_a + 16)), 1u);     // QCtl::done
         }
     } else {
         // =============================== consumers ===============================
@@ -469,22 +479,19 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         if (kPrime) {                                        // nothing is queued: the consumers of column half 0 wait for the four
             if (cw < 4) {                                    // scanner warps of their rows (two per column half)
                 const uint32_t ctl_b = ctl_a + 4u * (uint32_t)sizeof(QCtl);
-                while (lds_u32_acquire(ctl_a + 8) != 2u || lds_u32_acquire(ctl_b + 8) != 2u) __nanosleep(200);
+                while (lds_u32_acquire(ctl_a + 16) != 2u || lds_u32_acquire(ctl_b + 16) != 2u) __nanosleep(200);
             }
         } else
         for (;;) {
-            // lanes 0..15 look at ring 0, lanes 16..31 at ring 1: the leading ready entries of each (ring order)
+            // lanes 0..15 take entries of ring 0, lanes 16..31 of ring 1: up to 16 published entries of each (ring order)
             const int sub = lane >> 4;
+            const int n0 = min(16, (int)(lds_u32_acquire(ctl_a + 8) - head));
+            const int n1 = min(16, (int)(lds_u32_acquire(ctl_a + 12) - head1));
             const unsigned g = (sub ? head1 : head) + (unsigned)(lane & 15);
             const uint32_t ea = q_a + (uint32_t)(sub * Q_SUB + (int)(g % Q_SUB)) * Q_ENTRY;
-            const bool ready = lds_u32_acquire(ea + 72) == g / Q_SUB + 1u;
-            const unsigned rb = __ballot_sync(kFull, ready);
-            const unsigned r0 = rb & 0xffffu, r1 = rb >> 16;
-            const int n0 = (r0 == 0xffffu) ? 16 : __ffs(~r0) - 1;
-            const int n1 = (r1 == 0xffffu) ? 16 : __ffs(~r1) - 1;
             if (n0 + n1 == 0) {
                 if (saw_done) break;                                   // nothing was published before the producers finished
-                if (lds_u32_acquire(ctl_a + 8) == 2u) { saw_done = true; continue; }   // look once more: entries precede `done`
+                if (lds_u32_acquire(ctl_a + 16) == 2u) { saw_done = true; continue; }   // look once more: entries precede `done`
                 __nanosleep(32);
                 continue;
             }
