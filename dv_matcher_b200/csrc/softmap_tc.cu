@@ -40,7 +40,7 @@ constexpr int TC_MAX_SPLIT = 4;
 constexpr int TC_CHUNK = 16;               // columns per min-tree
 constexpr int TC_PRIME_STRIDE = 10;        // priming pass: every 10th tile.  Measured at 4 x 50k x 50k (prime + sweep, ms): stride 16: 3.24,
                                            // 12: 3.18, 10: 3.155, 8: 3.15; <= 6: thresholds so tight that rows run out of candidates (slow path)
-constexpr int TC_PRIME_MIN_TILES = 64; 
+constexpr int TC_PRIME_MIN_TILES = 16;      // ... when the sweep has at least this many tiles (M >= 4k): below, the sample is too small
 constexpr int TC_PREP_ROWS = 32;           // rows per block of the operand preparation (8 warps x 4 rows)     // ... when the sweep has at least this many tiles (M >= 16k)
 
 
@@ -255,6 +255,7 @@ __device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase
         sts_v2(ea + 64, __int_as_float(row_in_q), __int_as_float(cbase));
     }
     tail += (unsigned)n;
+    if (n >= 8) { ring_publish(head_a + 8, tail, lane); pub = tail; }   // flood (start-up, dense softmax windows): do not sit on the entries
 }
 
 // priming pass: the scanner thread keeps the KP smallest CHUNK MINIMA it has seen in a sorted register list (a branch-free
