@@ -1,10 +1,12 @@
 // tcgen05 candidate pass of the fused soft/hard map (sm_100a).
 //
-// Per CTA: a 256-row block of X (two UMMA M=128 sub-blocks, 16-bit, TMA, resident for the whole sweep)
-// against a stream of 128-column tiles of Y (TMA ring); every Y tile feeds TWO tcgen05.mma chains
-// (M=128, N=128, K = C + 16) whose fp32 accumulators live in TMEM (2 stages x 2 sub-blocks x 128 columns
-// = all 512 columns).  Sharing the Y tile between the two sub-blocks halves the L2 -> SM operand stream
-// (36 KB per 1152 tensor cycles = 31 B/clk/SM, under the ~42 B/clk/SM the L2 sustains chip-wide).
+// Per CTA PAIR (cluster of 2, tcgen05 cta_group::2): a 256-row block of X -- each CTA keeps ITS 128 rows (16-bit, TMA)
+// resident for the whole sweep -- against a stream of 256-column tiles of Y, of which each CTA stages ITS 128 columns
+// (3-stage TMA ring).  One tcgen05.mma.cta_group::2 chain per tile (M = 256 over the pair, N = 256, K = C + 16) with
+// fp32 accumulators in TMEM (2 stages x 256 columns = all 512 columns of each CTA).  Per CTA the MMAs read 4 KB of A
+// and 4 KB of B per 128 tensor cycles = 64 B/clk of shared-memory bandwidth (two single-CTA M=128 x N=128 chains read
+// 128 B/clk, everything an SM has); the L2 -> SM operand stream is 36 KB per CTA and tile = 31 B/clk/SM, under the
+// ~42 B/clk/SM the L2 sustains chip-wide.
 //
 // The norm is folded into the GEMM: operand rows are  A = [x~, 1, 1, 1, 0..]  and  B = [-y~, h_hi, h_mid, h_lo, 0..]
 // with h = |y~|^2 / 2 split into three 16-bit terms, so the accumulator IS the selection key
@@ -13,11 +15,11 @@
 // (0.5-1 instruction per entry) decides whether any entry of the chunk can matter (a top-16 candidate or a
 // term inside the softmax window); only those chunks take the slow path.
 //
-// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane),
-// warps 2..17 = epilogue: TMEM lane quarter = warp % 4 (hardware rule), group = (warp - 2) / 4 selects
-// (sub-block, column half).  One thread = one row x 64 columns of every tile.
-// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), all mbarriers; no
-// CTA-wide barrier inside the sweep.
+// Warp roles (832 threads per CTA): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer, one lane, leader CTA),
+// warps 2..17 = scanners: TMEM lane quarter = warp % 4 (hardware rule), column group = (warp - 2) / 4: one thread = one
+// row x 64 columns of every tile; warps 18..25 = consumers (32 rows x column half of the tile each).
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> scanners), all mbarriers, signalled across the
+// pair by multicast commits / remote arrives; no CTA-wide barrier inside the sweep.
 #include <cuda.h>
 #include <stdlib.h>
 #include "softmap.cuh"
@@ -162,17 +164,18 @@ struct TcParams {
 // 16 scanner warps (TMEM lane quarter = warp % 4; (sub-block, column half) from the warp's group of four): one
 // thread = one row x 64 columns of every tile, read with software-pipelined tcgen05.ld.  Per 16-column chunk a
 // min-tree (8 three-input min instructions) gives the chunk minimum; if it is below the row's published bound thr_hi
-// the lane copies the WHOLE chunk (16 keys, row, first column) into its consumer's queue in shared memory -- ~20
+// the lane copies the WHOLE chunk (16 keys, row, first column) into its warp's ring in shared memory -- ~20
 // uniform instructions per warp and chunk, no per-entry work, no per-thread lists.  Scanner cost is therefore almost
 // independent of the data.
 //
-// 8 consumer warps (one per 32 rows = sub-block x TMEM lane quarter) drain the queues with ONE LANE PER QUEUE ENTRY
-// (full lane utilisation whatever the rows are): the entry's keys below the bound replace the worst entry of the
-// row's K-entry list (shared memory) or add their softmax term exp2(-a2 (d - r)) to the row's mass; the lane then
-// publishes the row's new bound thr_hi = max(list threshold, softmax-window bound).  Entries of the same row inside
-// one batch of 32 are serialised in queue order (__match_any_sync).  The queue is a ring with a release/acquire
-// sequence word per slot; producers reserve slots with one warp-aggregated atomicAdd and wait for space, the
-// consumer never waits for a producer, so the protocol cannot deadlock.
+// 8 consumer warps (one per 32 rows x column half of the tile: a row has one list per column half) drain the rings of
+// their two scanner warps with ONE LANE PER ENTRY (full lane utilisation whatever the rows are): the entry's keys below
+// the bound replace the worst entry of the row's K-entry list (shared memory) or add their softmax term
+// exp2(-a2 (d - r)) to the row's mass; the lane then publishes the row's new bound thr_hi = max(list threshold,
+// softmax-window bound).  Entries of the same row inside one batch are serialised (__match_any_sync).  Every scanner
+// warp owns a single-producer ring (tail in a register, no atomic) and publishes its entries with one fence + tail
+// store per tile; it waits for space only after publishing what it holds, the consumer never waits for a producer, so
+// the protocol cannot deadlock.
 //
 // The list threshold of a row starts from the PRIMING pass (8th smallest chunk minimum of a 1/10 column sample ~ rank 80) and
 // is shared between column-split CTAs via atomicMin in global memory.  Whatever the thresholds were, every column a
