@@ -99,6 +99,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* __restric
 // is what makes a single barrier per iteration sufficient.  Selection rule ((value desc, index asc)) and arithmetic
 // are those of fps_kernel, so the node lists stay bit-identical to the reference.
 // ------------------------------------------------------------------------------------------------
+constexpr int FPSC_SMEM_PPT = 14;  // shared-memory variant: 14 x 1024 x 16 B = 224 KB per CTA
 constexpr int FPSC_PPT = 8;       // 8 x 4 registers of point state per thread (1024-thread CTAs have 64 registers)
 
 struct __align__(16) FpsSlot { float v; int i; float x, y, z; float pad[3]; };   // 32 bytes: 16-byte aligned remote stores
@@ -117,9 +118,13 @@ __device__ __forceinline__ void fps_cluster_barrier() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int CS>
+// kSmem: the CTA's points and running distances live in dynamic shared memory ([ppt][1024] per array, conflict-free)
+// instead of registers: up to 14 points per thread = 229376 points per 16-CTA cluster (a 200k cloud: 3.1 s -> see DESIGN).
+// Same arithmetic and the same ascending visiting order per thread: identical node lists.
+template <int CS, bool kSmem>
 __global__ void __launch_bounds__(FPS_THREADS)
-fps_cluster_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* __restrict__ start, int64_t* __restrict__ out) {
+fps_cluster_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* __restrict__ start, int64_t* __restrict__ out, int ppt) {
+    extern __shared__ float fps_dyn[];
     __shared__ float s_v[32];
     __shared__ int s_i[32];
     __shared__ FpsSlot s_slot[2][16];                        // [parity][rank]
@@ -129,11 +134,21 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* _
     const float* P = xyz + (size_t)b * N * 3;
     // point p of the cloud belongs to CTA (p / 1024) % CS, thread p % 1024, register (p / 1024) / CS
     float px[FPSC_PPT], py[FPSC_PPT], pz[FPSC_PPT], pd[FPSC_PPT];
+    float* sx = fps_dyn; float* sy = sx + ppt * FPS_THREADS; float* sz = sy + ppt * FPS_THREADS; float* sd = sz + ppt * FPS_THREADS;
+    if (kSmem) {
+        for (int q = 0; q < ppt; ++q) {
+            const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
+            const int e = q * FPS_THREADS + tid;
+            sx[e] = sy[e] = sz[e] = 0.f; sd[e] = -1.f;
+            if (p < N) { sx[e] = P[p * 3]; sy[e] = P[p * 3 + 1]; sz[e] = P[p * 3 + 2]; sd[e] = 1e10f; }
+        }
+    } else {
 #pragma unroll
-    for (int q = 0; q < FPSC_PPT; ++q) {
-        const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
-        px[q] = py[q] = pz[q] = 0.f; pd[q] = -1.f;            // padding never wins the arg-max
-        if (p < N) { px[q] = P[p * 3]; py[q] = P[p * 3 + 1]; pz[q] = P[p * 3 + 2]; pd[q] = 1e10f; }
+        for (int q = 0; q < FPSC_PPT; ++q) {
+            const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
+            px[q] = py[q] = pz[q] = 0.f; pd[q] = -1.f;            // padding never wins the arg-max
+            if (p < N) { px[q] = P[p * 3]; py[q] = P[p * 3 + 1]; pz[q] = P[p * 3 + 2]; pd[q] = 1e10f; }
+        }
     }
     int far = (int)start[b];
     float cx = __ldg(P + far * 3), cy = __ldg(P + far * 3 + 1), cz = __ldg(P + far * 3 + 2);
@@ -141,13 +156,27 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* _
     for (int it = 0; it < K; ++it) {
         if (rank == 0 && tid == 0) out[(size_t)b * K + it] = far;
         float bv = -1.f; int bi = 0x7fffffff; float bx = 0.f, by = 0.f, bz = 0.f;
+        if (kSmem) {
+            for (int q = 0; q < ppt; ++q) {
+                const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
+                const int e = q * FPS_THREADS + tid;
+                if (p < N) {
+                    const float x = sx[e], y = sy[e], z = sz[e];
+                    float dd = sd[e];
+                    const float d = fps_d2(x, y, z, cx, cy, cz);
+                    if (d < dd) { dd = d; sd[e] = d; }
+                    if (dd > bv) { bv = dd; bi = p; bx = x; by = y; bz = z; }
+                }
+            }
+        } else {
 #pragma unroll
-        for (int q = 0; q < FPSC_PPT; ++q) {
-            const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
-            if (p < N) {
-                const float d = fps_d2(px[q], py[q], pz[q], cx, cy, cz);
-                if (d < pd[q]) pd[q] = d;
-                if (pd[q] > bv) { bv = pd[q]; bi = p; bx = px[q]; by = py[q]; bz = pz[q]; }     // ascending p per thread: strict '>' keeps the first
+            for (int q = 0; q < FPSC_PPT; ++q) {
+                const int p = (q * CS + (int)rank) * FPS_THREADS + tid;
+                if (p < N) {
+                    const float d = fps_d2(px[q], py[q], pz[q], cx, cy, cz);
+                    if (d < pd[q]) pd[q] = d;
+                    if (pd[q] > bv) { bv = pd[q]; bi = p; bx = px[q]; by = py[q]; bz = pz[q]; }     // ascending p per thread: strict '>' keeps the first
+                }
             }
         }
         // warp arg-max (value desc, index asc), carrying the coordinates
@@ -190,17 +219,20 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int K, const int64_t* _
     fps_cluster_barrier();                                     // nobody exits while a peer may still write into its shared memory
 }
 
-template <int CS>
+template <int CS, bool kSmem>
 static int launch_fps_cluster(const float* xyz, int B, int N, int K, const int64_t* start, int64_t* out, cudaStream_t st) {
-    auto kern = fps_cluster_kernel<CS>;
+    auto kern = fps_cluster_kernel<CS, kSmem>;
     if (CS > 8) DVM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const int ppt = kSmem ? ceil_div(N, CS * FPS_THREADS) : 0;
+    const size_t dyn = (size_t)ppt * FPS_THREADS * 4 * sizeof(float);
+    if (kSmem) DVM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(B * CS); cfg.blockDim = dim3(FPS_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = dim3(B * CS); cfg.blockDim = dim3(FPS_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    DVM_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, K, start, out));
+    DVM_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, K, start, out, ppt));
     count_launch();
     return 0;
 }
@@ -272,8 +304,10 @@ extern "C" int dvm_fps(const float* xyz, int B, int N, int K, const int64_t* sta
     // few big clouds: a cluster of CTAs per cloud (points in registers, results exchanged through distributed shared
     // memory); many small clouds: one CTA each already fills the machine
     if (N > FPS_THREADS * FPS_PPT && (long long)B * 8 <= 4 * kNumSM) {      // one CTA holds <= 8192 points in registers (1.1 us / iteration)
-        if (N <= 8 * FPS_THREADS * FPSC_PPT) return launch_fps_cluster<8>(xyz, B, N, K, start, out, st);
-        if (N <= 16 * FPS_THREADS * FPSC_PPT) return launch_fps_cluster<16>(xyz, B, N, K, start, out, st);
+        if (N <= 8 * FPS_THREADS * FPSC_PPT) return launch_fps_cluster<8, false>(xyz, B, N, K, start, out, st);
+        if (N <= 16 * FPS_THREADS * FPSC_PPT) return launch_fps_cluster<16, false>(xyz, B, N, K, start, out, st);
+        if (N <= 16 * FPS_THREADS * FPSC_SMEM_PPT && (long long)B * 16 <= kNumSM)     // points in shared memory: <= 229376 per cloud
+            return launch_fps_cluster<16, true>(xyz, B, N, K, start, out, st);
     }
     if (N <= FPS_THREADS * FPS_PPT) {
         fps_kernel<true><<<B, FPS_THREADS, 0, st>>>(xyz, N, K, start, out, nullptr);

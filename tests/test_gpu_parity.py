@@ -613,6 +613,19 @@ def test_fps_cluster_kernel_matches_single_cta_kernel():
         assert (got[b] == ref).all()
 
 
+def test_fps_cluster_shared_memory_variant_matches_oracle():
+    """131072 < N <= 229376: the 16-CTA cluster keeps its points in shared memory; same node list as the oracle."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    n = 140001
+    xyz = torch.rand(1, n, 3, generator=g)
+    xyz[0, 100000] = xyz[0, 7]                               # duplicate points: first-index tie-break
+    start = torch.tensor([n - 1])
+    got = ops.fps(_cuda(xyz), 300, start).cpu().numpy()
+    ref = ogr.farthest_point_sample(xyz[0].numpy(), 300, n - 1)
+    assert (got[0] == ref).all()
+
+
 # ------------------------------------------------------------------------------------------------
 # decoder MLP on tensor cores (3xTF32): fp32-equivalent, tolerance 1e-5 relative to the output scale
 # ------------------------------------------------------------------------------------------------
