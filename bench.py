@@ -148,8 +148,12 @@ def timed_loop(fn, steps, warmup, dist, device):
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1)
+    timed_loop.rank_ms = [ms]
     if dist is not None:
         t = torch.tensor([ms], device=device)
+        allr = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(allr, t)
+        timed_loop.rank_ms = [a.item() for a in allr]          # diagnostic: the spread over ranks (the value uses the max)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
         dist.barrier()
@@ -212,13 +216,14 @@ def run_b200(args):
         sampler.start()
         lw = lib.dvm_launch_count()
         ms = timed_loop(step, steps, 0, dist, device)
+        rank_ms = [round(v / steps, 3) for v in timed_loop.rank_ms]
         launches = lib.dvm_launch_count() - lw
         sampler.stop_flag = True
         sampler.join(timeout=2)
         tot, cnt = ctypes.c_double(0), ctypes.c_int(0)
         lib.dvm_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
         lib.dvm_profile_enable(0)
-        res = dict(ms=ms, launches=launches, nring=nring, graph_cold_s=graph_cold_s, clocks=sampler.summary(),
+        res = dict(ms=ms, launches=launches, nring=nring, graph_cold_s=graph_cold_s, clocks=sampler.summary(), rank_ms=rank_ms,
                    cand_ms=tot.value, cand_launches=cnt.value)
         # stats of the last step: rows the 16-bit pass could not certify
         from dv_matcher_b200 import ops
@@ -276,7 +281,7 @@ def run_b200(args):
         e2e=dict(value=B * world * e2e["steps"] / (e2e["ms"] * 1e-3), unit=UNIT, h2d_bytes_per_step=e2e["h2d"], d2h_bytes_per_step=e2e["d2h"]),
         gpu_launches=int(main["launches"]), clocks=main["clocks"],
         extra=dict(uncertified_rows_frac=main["uncertified_rows_frac"], graph_build_cold_s_per_pair=main["graph_cold_s"],
-                   sim_tflops=achieved),
+                   sim_tflops=achieved, ms_per_step_by_rank=main["rank_ms"]),
     )
     if not args.no_5k:
         s5 = bench_size(4995, 16, max(10, args.steps), 3, with_e2e=False)
