@@ -223,7 +223,13 @@ def run_b200(args):
         tot, cnt = ctypes.c_double(0), ctypes.c_int(0)
         lib.dvm_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
         lib.dvm_profile_enable(0)
+        clocks_by_rank = None
+        if dist is not None:                       # diagnostic: median SM clock and throttle reasons of every rank's GPU
+            objs = [None] * world
+            dist.all_gather_object(objs, sampler.summary())
+            clocks_by_rank = [[o.get("sm_mhz"), o.get("reasons")] for o in objs]
         res = dict(ms=ms, launches=launches, nring=nring, graph_cold_s=graph_cold_s, clocks=sampler.summary(), rank_ms=rank_ms,
+                   clocks_by_rank=clocks_by_rank,
                    cand_ms=tot.value, cand_launches=cnt.value)
         # stats of the last step: rows the 16-bit pass could not certify
         from dv_matcher_b200 import ops
@@ -281,7 +287,7 @@ def run_b200(args):
         e2e=dict(value=B * world * e2e["steps"] / (e2e["ms"] * 1e-3), unit=UNIT, h2d_bytes_per_step=e2e["h2d"], d2h_bytes_per_step=e2e["d2h"]),
         gpu_launches=int(main["launches"]), clocks=main["clocks"],
         extra=dict(uncertified_rows_frac=main["uncertified_rows_frac"], graph_build_cold_s_per_pair=main["graph_cold_s"],
-                   sim_tflops=achieved, ms_per_step_by_rank=main["rank_ms"]),
+                   sim_tflops=achieved, ms_per_step_by_rank=main["rank_ms"], clocks_by_rank=main["clocks_by_rank"]),
     )
     if not args.no_5k:
         s5 = bench_size(4995, 16, max(10, args.steps), 3, with_e2e=False)
