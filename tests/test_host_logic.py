@@ -143,3 +143,34 @@ def test_off_vts_and_cache_round_trip(tmp_path):
     evalio.save_cache(str(c), [torch.from_numpy(pts)], ["a"], [torch.arange(5)], [torch.zeros(37, 37, dtype=torch.float64)])
     v, names, fps, dist = evalio.load_cache(str(c))
     assert names == ["a"] and torch.equal(v[0], torch.from_numpy(pts)) and fps[0].tolist() == [0, 1, 2, 3, 4] and dist[0].dtype == torch.float64
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py contract pieces that run without a GPU
+# ------------------------------------------------------------------------------------------------
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` = the oracle port timed on the host cores: one JSON line with the reference-arm keys."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--n", "600", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("shape pairs/sec") and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+def test_bench_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm prints why and measures nothing."""
+    import subprocess
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert "no CPU fallback" in (out.stdout + out.stderr)
+    assert not any(l.startswith("{") for l in out.stdout.splitlines())
