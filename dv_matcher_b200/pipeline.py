@@ -16,6 +16,17 @@ from .deformation_graph import BatchedGraph, build_graphs, deform_batched
 from .geometry import rotation_6d_to_matrix
 
 _IDEN6 = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+_IDEN6_DEV = {}
+
+
+def _iden6(device):
+    """The identity offset of models/loss.py:1259-1262 as a cached device constant: building it per step from a Python
+    list is a blocking host-to-device copy, i.e. a full stream synchronisation in the middle of every step."""
+    t = _IDEN6_DEV.get(device)
+    if t is None:
+        t = torch.tensor(_IDEN6, device=device, dtype=torch.float32)
+        _IDEN6_DEV[device] = t
+    return t
 
 
 def cat_graphs(g1, g2):
@@ -52,7 +63,7 @@ def match_deform(feat1, feat2, verts1, verts2, graphs, deformer, alpha=100.0, k_
     idx_tgt = torch.cat([idx_self[B:], idx_self[:B]])
     fps = graphs.nodes_idx
     deformations = deformer.forward_fused(fsrc, ftgt, idx_self, idx_tgt, src, vt, sm, fps)     # [2B,K,9]
-    iden = torch.tensor(_IDEN6, device=src.device, dtype=torch.float32)
+    iden = _iden6(src.device)
     R = rotation_6d_to_matrix(deformations[..., 3:] + iden)               # models/loss.py:1258-1264
     T = deformations[..., :3].contiguous()
     deformed, arap, sr = deform_batched(src, graphs, R, T)                 # models/loss.py:1269-1273
