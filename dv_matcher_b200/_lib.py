@@ -23,6 +23,7 @@ SIGNATURES = {
     "dvm_launch_count": (ctypes.c_longlong, []),
     "dvm_profile_enable": (c_int, [c_int]),
     "dvm_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
+    "dvm_profile_read_channel": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
     "dvm_softmap_workspace_bytes": (c_size_t, [c_int] * 5),
     "dvm_softmap_fwd": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_float] + [c_int] * 3 + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "dvm_softmap_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
@@ -45,6 +46,12 @@ SIGNATURES = {
     "dvm_arap_workspace_bytes": (c_size_t, [c_int] * 2),
     "dvm_arap_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "dvm_arap_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 3),
+    "dvm_node_table": (c_int, [c_void_p] * 3 + [c_int] * 2 + [c_void_p] * 2),
+    "dvm_node_table_from_d9": (c_int, [c_void_p] * 2 + [c_int] * 2 + [c_void_p] * 4),
+    "dvm_skin_fwd_packed": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 2),
+    "dvm_skin_bwd_csr": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p] * 3),
+    "dvm_arap_packed_workspace_bytes": (c_size_t, [c_int] * 2),
+    "dvm_arap_fwd_packed": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "dvm_gather_conv_fwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 2),
     "dvm_gather_conv_bwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 4),
     "dvm_linear_act_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
@@ -84,11 +91,14 @@ def check(rc, what):
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
-def ptr(t):
-    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+def ptr(t, dtype=None):
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL); `dtype` asserts what the kernel will read."""
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), "dv_matcher_b200 kernels need contiguous CUDA tensors"
+    if not (t.is_cuda and t.is_contiguous()):
+        raise RuntimeError("dv_matcher_b200 kernels need contiguous CUDA tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"dv_matcher_b200: expected a {dtype} tensor, got {t.dtype}")
     return t.data_ptr()
 
 
@@ -101,6 +111,10 @@ def require_device(t):
     if not t.is_cuda:
         raise RuntimeError("dv_matcher_b200: tensors must live on a CUDA (sm_100) device; there is no CPU path")
     dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if dev != torch.cuda.current_device():
+        # the library launches on the CURRENT device and stream (one process per GPU): refuse instead of launching elsewhere
+        raise RuntimeError(f"dv_matcher_b200: tensor lives on cuda:{dev} but the current device is cuda:{torch.cuda.current_device()}; "
+                           "call torch.cuda.set_device first (one process per GPU)")
     if dev not in _device_ok:
         with torch.cuda.device(dev):
             check(load().dvm_device_check(), "dvm_device_check")
@@ -113,11 +127,15 @@ class _Workspace:
 
     def __init__(self):
         self.buf = {}
+        self.keep_retired = False      # set once a CUDA graph has been captured: its kernels hold raw workspace addresses
+        self.retired = []
 
     def get(self, nbytes, device, tag="default"):
         key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
+            if b is not None and self.keep_retired:
+                self.retired.append(b)
             b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self.buf[key] = b
         return b

@@ -18,32 +18,51 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(); }
 
-// CUDA-event brackets around the dominant (candidate-pass) kernel, for bench.py's live roofline.
+// CUDA-event brackets for bench.py's live rooflines.  Channel 0 = the dominant (candidate-pass) kernels,
+// channel 1 = the whole fused op dvm_softmap_fwd (prep + prime + sweep + finalize + rescue); the brackets of different
+// channels nest.  Events are recorded on the stream the kernels are launched on.
+constexpr int kProfChannels = 2;
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
-static std::vector<cudaEvent_t> g_prof_ev;      // start/stop pairs
-static size_t g_prof_used = 0;
-static bool g_prof_open = false;
+struct ProfChannel { std::vector<cudaEvent_t> ev; size_t used = 0; bool open = false; };
+static ProfChannel g_prof[kProfChannels];
 constexpr size_t kProfMaxPairs = 4096;
-void prof_begin(cudaStream_t st) {
+void prof_begin(cudaStream_t st, int ch) {
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    if (g_prof_used / 2 >= kProfMaxPairs) return;
-    if (g_prof_ev.size() < g_prof_used + 2) {
+    ProfChannel& c = g_prof[ch];
+    if (c.used / 2 >= kProfMaxPairs) return;
+    if (c.ev.size() < c.used + 2) {
         cudaEvent_t a, b;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
-        g_prof_ev.push_back(a); g_prof_ev.push_back(b);
+        c.ev.push_back(a); c.ev.push_back(b);
     }
-    cudaEventRecord(g_prof_ev[g_prof_used], st);
-    g_prof_open = true;
+    cudaEventRecord(c.ev[c.used], st);
+    c.open = true;
 }
-void prof_end(cudaStream_t st) {
+void prof_end(cudaStream_t st, int ch) {
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    if (!g_prof_open) return;
-    g_prof_open = false;
-    cudaEventRecord(g_prof_ev[g_prof_used + 1], st);
-    g_prof_used += 2;
+    ProfChannel& c = g_prof[ch];
+    if (!c.open) return;
+    c.open = false;
+    cudaEventRecord(c.ev[c.used + 1], st);
+    c.used += 2;
+}
+static int prof_read(int ch, double* total_ms, int* brackets) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfChannel& c = g_prof[ch];
+    double tot = 0.0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < c.used; i += 2) {
+        float ms = 0.f;
+        DVM_CUDA(cudaEventSynchronize(c.ev[i + 1]));
+        DVM_CUDA(cudaEventElapsedTime(&ms, c.ev[i], c.ev[i + 1]));
+        tot += ms; ++n;
+    }
+    if (total_ms) *total_ms = tot;
+    if (brackets) *brackets = n;
+    return 0;
 }
 }  // namespace dvm
 
@@ -51,22 +70,13 @@ extern "C" long long dvm_launch_count(void) { return dvm::launches(); }
 extern "C" int dvm_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(dvm::g_prof_mu);
     dvm::g_prof_on = on != 0;
-    dvm::g_prof_used = 0;
+    for (auto& c : dvm::g_prof) { c.used = 0; c.open = false; }
     return 0;
 }
-extern "C" int dvm_profile_read(double* total_ms, int* brackets) {
-    std::lock_guard<std::mutex> lk(dvm::g_prof_mu);
-    double tot = 0.0;
-    int n = 0;
-    for (size_t i = 0; i + 1 < dvm::g_prof_used; i += 2) {
-        float ms = 0.f;
-        DVM_CUDA(cudaEventSynchronize(dvm::g_prof_ev[i + 1]));
-        DVM_CUDA(cudaEventElapsedTime(&ms, dvm::g_prof_ev[i], dvm::g_prof_ev[i + 1]));
-        tot += ms; ++n;
-    }
-    if (total_ms) *total_ms = tot;
-    if (brackets) *brackets = n;
-    return 0;
+extern "C" int dvm_profile_read(double* total_ms, int* brackets) { return dvm::prof_read(0, total_ms, brackets); }
+extern "C" int dvm_profile_read_channel(int channel, double* total_ms, int* brackets) {
+    if (channel < 0 || channel >= dvm::kProfChannels) { dvm::set_error("dvm_profile_read_channel: bad channel %d", channel); return DVM_ERR_INVALID_ARG; }
+    return dvm::prof_read(channel, total_ms, brackets);
 }
 
 extern "C" int dvm_version(void) { return DVM_VERSION; }

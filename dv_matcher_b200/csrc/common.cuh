@@ -20,8 +20,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 void set_error(const char* fmt, ...);
 void count_launch();                       // every kernel launch of the library is counted (dvm_launch_count)
-void prof_begin(cudaStream_t st);          // optional CUDA-event bracket around the dominant kernel
-void prof_end(cudaStream_t st);
+void prof_begin(cudaStream_t st, int ch = 0);   // optional CUDA-event brackets: channel 0 = the dominant (candidate-pass)
+void prof_end(cudaStream_t st, int ch = 0);     // kernels, channel 1 = the whole fused op dvm_softmap_fwd
 
 #define DVM_CHECK_ARG(cond, ...)                                     \
     do { if (!(cond)) { dvm::set_error(__VA_ARGS__); return DVM_ERR_INVALID_ARG; } } while (0)

@@ -750,12 +750,11 @@ extern "C" size_t dvm_softmap_workspace_bytes(int B, int N, int M, int C, int pr
     return softmap_ws_layout(nullptr, 0, B, N, M, C, prec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
-extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
-                               int B, int N, int M, int C, int Dv, float alpha, int topk, int mode, int prec,
-                               int64_t* argmin, int32_t* top_idx, float* top_w, float* top_d,
-                               float* row_min, float* row_sum, float* PiV, int32_t* stats,
-                               void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int softmap_fwd_impl(const float* X, const float* Y, const float* V,
+                            int B, int N, int M, int C, int Dv, float alpha, int topk, int mode, int prec,
+                            int64_t* argmin, int32_t* top_idx, float* top_w, float* top_d,
+                            float* row_min, float* row_sum, float* PiV, int32_t* stats,
+                            void* ws, size_t ws_bytes, cudaStream_t st) {
     DVM_CHECK_ARG(X && Y && top_idx && top_d, "dvm_softmap_fwd: X, Y, top_idx, top_d must be non-null");
     DVM_CHECK_ARG(B > 0 && N > 0 && M > 0, "dvm_softmap_fwd: empty problem (B=%d N=%d M=%d)", B, N, M);
     DVM_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 256, "dvm_softmap_fwd: C=%d must be a multiple of 4 and <= 256", C);
@@ -832,4 +831,17 @@ extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
     fa.row_list = list2; fa.row_count = count2; fa.flag_list = nullptr; fa.flag_count = nullptr; fa.flag_thr = nullptr; fa.flag_r = nullptr;
     fa.tie_count = st_out + 1;
     return launch_finalize(fa, soft, rows, st);
+}
+
+extern "C" int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
+                               int B, int N, int M, int C, int Dv, float alpha, int topk, int mode, int prec,
+                               int64_t* argmin, int32_t* top_idx, float* top_w, float* top_d,
+                               float* row_min, float* row_sum, float* PiV, int32_t* stats,
+                               void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    prof_begin(st, 1);                 // channel 1: the whole fused op (what north_star's tensor-peak target is quoted on)
+    const int rc = softmap_fwd_impl(X, Y, V, B, N, M, C, Dv, alpha, topk, mode, prec, argmin, top_idx, top_w, top_d,
+                                    row_min, row_sum, PiV, stats, ws, ws_bytes, st);
+    prof_end(st, 1);
+    return rc;
 }

@@ -21,6 +21,23 @@ from .geometry import rotation_6d_to_matrix  # noqa: F401  (re-exported for call
 
 
 @dataclass
+class GraphPack:
+    """HBM-shaped copy of the graph tensors the per-step kernels stream (static per shape; see csrc/deform_packed.cu)."""
+    nodes_xyz: torch.Tensor     # f32   [B,K,3]   g = xyz[nodes_idx]
+    vorder: torch.Tensor        # int32 [B,N]     vertices in Morton order
+    s_infl: torch.Tensor        # int32 [B,3,N]   influence lists of vertex vorder[i], slot-major
+    s_w: torch.Tensor           # f32   [B,3,N]
+    norder: torch.Tensor        # int32 [B,K]     nodes in Morton order
+    s_ring: torch.Tensor        # int32 [B,9,K]   ring of node norder[i], slot-major
+    csr_ptr: torch.Tensor       # int32 [B,K+1]   vertices influenced by each node ...
+    csr_vert: torch.Tensor      # int32 [B,3N]    ... ascending vertex id
+    csr_w: torch.Tensor         # f32   [B,3N]
+
+    def tensors(self):
+        return (self.nodes_xyz, self.vorder, self.s_infl, self.s_w, self.norder, self.s_ring, self.csr_ptr, self.csr_vert, self.csr_w)
+
+
+@dataclass
 class BatchedGraph:
     """Graph tensors of B clouds (same N, K): everything stays on the device."""
     nodes_idx: torch.Tensor     # int64 [B,K]  vertex index of every node (== `num_nodes_all` of the reference driver)
@@ -29,6 +46,24 @@ class BatchedGraph:
     weights: torch.Tensor       # f32  [B,N,3]
     ring: torch.Tensor          # int64 [B,K,9] node index space, self first
     sigma: torch.Tensor         # f64  [B]
+    pack: GraphPack = None      # streaming layout of the same graph (built by `pack_graph`)
+
+    def tensors(self):
+        base = (self.nodes_idx, self.influence, self.dists, self.weights, self.ring, self.sigma)
+        return base + (self.pack.tensors() if self.pack is not None else ())
+
+    @staticmethod
+    def from_tensors(ts):
+        ts = list(ts)
+        return BatchedGraph(*ts[:6], pack=GraphPack(*ts[6:]) if len(ts) > 6 else None)
+
+    @staticmethod
+    def cat(graphs):
+        return BatchedGraph.from_tensors([torch.cat(parts) for parts in zip(*[g.tensors() for g in graphs])])
+
+    def select(self, i):
+        """Graph of cloud i as a batch of one."""
+        return BatchedGraph.from_tensors([t[i:i + 1] for t in self.tensors()])
 
 
 def draw_fps_start(B, N):
@@ -45,6 +80,45 @@ def farthest_point_sample(xyz, npoint, start=None):
     return ops.fps(xyz, npoint, start)
 
 
+def _morton_order(p):
+    """argsort of 30-bit Morton codes of points p [B,n,3] (per-cloud bounding box), int32 [B,n]."""
+    lo = p.amin(1, keepdim=True)
+    ext = (p.amax(1, keepdim=True) - lo).clamp_min(1e-20)
+    q = ((p - lo) / ext * 1023.0).long().clamp_(0, 1023)
+
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        return (v | (v << 2)) & 0x09249249
+
+    code = spread(q[..., 0]) | (spread(q[..., 1]) << 1) | (spread(q[..., 2]) << 2)
+    return torch.argsort(code, dim=1, stable=True).to(torch.int32)
+
+
+def pack_graph(verts, nodes_idx, influence, weights, ring):
+    """Streaming layout of a graph (once per shape; plain torch ops -- this is graph construction, not the per-step path)."""
+    B, N, _ = verts.shape
+    K = nodes_idx.shape[1]
+    nodes_xyz = torch.gather(verts, 1, nodes_idx[..., None].expand(B, K, 3)).contiguous()
+    vorder = _morton_order(verts)
+    vo = vorder.long()
+    s_infl = torch.gather(influence, 1, vo[..., None].expand(B, N, 3)).transpose(1, 2).to(torch.int32).contiguous()
+    s_w = torch.gather(weights, 1, vo[..., None].expand(B, N, 3)).transpose(1, 2).contiguous()
+    norder = _morton_order(nodes_xyz)
+    no = norder.long()
+    rk = ring.shape[2]
+    s_ring = torch.gather(ring, 1, no[..., None].expand(B, K, rk)).transpose(1, 2).to(torch.int32).contiguous()
+    flat = influence.reshape(B, 3 * N)
+    order = torch.argsort(flat, dim=1, stable=True)                       # entries (v, k) sorted by node, ascending v within a node
+    csr_vert = (order // 3).to(torch.int32).contiguous()
+    csr_w = torch.gather(weights.reshape(B, 3 * N), 1, order).contiguous()
+    counts = torch.zeros(B, K, dtype=torch.int64, device=verts.device).scatter_add_(1, flat, torch.ones_like(flat))
+    csr_ptr = torch.zeros(B, K + 1, dtype=torch.int32, device=verts.device)
+    csr_ptr[:, 1:] = counts.cumsum(1).to(torch.int32)
+    return GraphPack(nodes_xyz, vorder, s_infl, s_w, norder, s_ring, csr_ptr, csr_vert, csr_w)
+
+
 def build_graphs(verts, start=None):
     """construct_graph_euclidean for a batch verts [B,N,3] (K = N // 2 nodes, 3 influences, ring of 9)."""
     B, N, _ = verts.shape
@@ -53,32 +127,51 @@ def build_graphs(verts, start=None):
     verts = verts.float().contiguous()
     nodes_idx = ops.fps(verts, N // 2, start)
     infl, dists, wts, ring, sigma = ops.graph_weights(verts, nodes_idx)
-    return BatchedGraph(nodes_idx, infl, dists, wts, ring, sigma)
+    return BatchedGraph(nodes_idx, infl, dists, wts, ring, sigma, pack_graph(verts, nodes_idx, infl, wts, ring))
 
 
 class _Deform(torch.autograd.Function):
     """(R [B,K,3,3], t [B,K,3]) -> warped [B,N,3], arap [B], sr [B]; geometry and graph carry no gradient."""
 
     @staticmethod
-    def forward(ctx, verts, R, t, nodes_idx, infl, wts, ring):
+    def forward(ctx, verts, R, t, graph, want_sr):
         verts, R, t = verts.float().contiguous(), R.float().contiguous(), t.float().contiguous()
-        warped = ops.skin_fwd(verts, nodes_idx, infl, wts, R, t)
-        arap, sr = ops.arap_fwd(verts, nodes_idx, ring, R, t)
-        ctx.save_for_backward(verts, R, t, nodes_idx, infl, wts, ring)
+        table = ops.node_table(R, t, graph.pack.nodes_xyz)
+        warped = ops.skin_fwd_packed(verts, graph.pack, table)
+        arap, sr = ops.arap_fwd_packed(graph.pack, table, want_sr)
+        ctx.save_for_backward(verts, R, t)
+        ctx.graph = graph
+        if sr is None:
+            sr = torch.zeros_like(arap)
         ctx.mark_non_differentiable(sr)
         return warped, arap, sr
 
     @staticmethod
     def backward(ctx, d_warped, d_arap, _d_sr):
-        verts, R, t, nodes_idx, infl, wts, ring = ctx.saved_tensors
-        dR, dt = ops.skin_bwd(verts, nodes_idx, infl, wts, d_warped.contiguous())
-        ops.arap_bwd(verts, nodes_idx, ring, R, t, d_arap.contiguous(), dR, dt)
-        return None, dR, dt, None, None, None, None
+        verts, R, t = ctx.saved_tensors
+        g = ctx.graph
+        dR, dt = ops.skin_bwd_csr(verts, g.pack, d_warped.contiguous())
+        ops.arap_bwd(verts, g.nodes_idx, g.ring, R, t, d_arap.contiguous(), dR, dt)
+        return None, dR, dt, None, None
 
 
-def deform_batched(verts, graph, R, t):
-    """Batched DeformationGraph_geod.forward: returns (warped [B,N,3], arap [B], sr [B])."""
-    return _Deform.apply(verts, R, t, graph.nodes_idx, graph.influence, graph.weights, graph.ring)
+def deform_batched(verts, graph, R, t, want_sr=True):
+    """Batched DeformationGraph_geod.forward: returns (warped [B,N,3], arap [B], sr [B]; zeros when want_sr is False --
+    no caller of the reference ever reads the smoothness term)."""
+    if graph.pack is None:
+        graph.pack = pack_graph(verts.float().contiguous(), graph.nodes_idx, graph.influence, graph.weights, graph.ring)
+    return _Deform.apply(verts, R, t, graph, want_sr)
+
+
+def deform_from_d9(verts, graph, d9, want_sr=False):
+    """Inference form fused with models/loss.py:1257-1264: d9 [B,K,9] is the Deformer output (t, 6D residual); the
+    identity offset, 6D -> R and the node-record packing are one kernel.  Returns (warped, arap, sr or None)."""
+    if graph.pack is None:
+        graph.pack = pack_graph(verts.float().contiguous(), graph.nodes_idx, graph.influence, graph.weights, graph.ring)
+    table = ops.node_table_from_d9(d9, graph.pack.nodes_xyz)
+    warped = ops.skin_fwd_packed(verts, graph.pack, table)
+    arap, sr = ops.arap_fwd_packed(graph.pack, table, want_sr)
+    return warped, arap, sr
 
 
 class DeformationGraph_geod(nn.Module):
@@ -159,8 +252,7 @@ def deformation_graph_node(verts1):
     dg_list = []
     for i in range(B):
         dg = DeformationGraph_geod()
-        dg._graph = BatchedGraph(g.nodes_idx[i:i + 1], g.influence[i:i + 1], g.dists[i:i + 1], g.weights[i:i + 1],
-                                 g.ring[i:i + 1], g.sigma[i:i + 1])
+        dg._graph = g.select(i)
         dg.max_neigh_num = 9
         dg.nodes_idx = _LazyNumpy(g.nodes_idx[i])
         dg.one_ring_neigh = _LazyNumpy(g.ring[i])

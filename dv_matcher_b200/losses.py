@@ -87,10 +87,16 @@ class _GraphDeformBase(nn.Module):
         self.frob_loss = FrobeniusLoss()
         self.chamfer_dist_3d = chamfer_3DDist()
         self.save_name = save_name
-        # graphs are a pure function of the geometry + the FPS start index: cache them per cloud identity
-        # ("warm" path).  Off by default so that every forward redraws the start like the reference does.
+        # graphs are a pure function of the geometry + the FPS start index: with cache_graphs = True they are cached under
+        # the keys the CALLER supplies per forward through `graph_keys = (key of verts1, key of verts2)` (e.g. the dataset
+        # indices of the two shape batches) -- tensor addresses are reused by the caching allocator and identify nothing.
+        # Off by default so that every forward redraws the start like the reference does.  Bounded (FIFO).
         self.cache_graphs = False
+        self.graph_keys = None
+        self.max_cached_graphs = 256
         self._graph_cache = {}
+        self._graph_slot = 0
+        self._iden6 = {}
 
     # -- pieces of the reference API -----------------------------------------------------------------
     def topk_pi(self, A):
@@ -104,15 +110,30 @@ class _GraphDeformBase(nn.Module):
         `num_nodes_all`, BatchedGraph) -- the second item replaces the reference's list of per-cloud objects."""
         key = None
         if self.cache_graphs:
-            key = (verts1.data_ptr(), tuple(verts1.shape), verts1._version)
+            if self.graph_keys is None:
+                raise RuntimeError("cache_graphs = True needs graph_keys = (key1, key2) identifying the two shape batches of this forward")
+            key = (self.graph_keys[self._graph_slot % 2], tuple(verts1.shape))
+            self._graph_slot += 1
             hit = self._graph_cache.get(key)
             if hit is not None:
                 return hit
         g = build_graphs(verts1.detach(), draw_fps_start(verts1.shape[0], verts1.shape[1]))
         out = (g.nodes_idx.float(), g)
         if key is not None:
+            if len(self._graph_cache) >= self.max_cached_graphs:
+                self._graph_cache.pop(next(iter(self._graph_cache)))
             self._graph_cache[key] = out
         return out
+
+    def _identity6(self, ref):
+        """[1,0,0,0,1,0] of models/loss.py:1259-1262 as a cached device constant (a per-step torch.tensor(list, device=...)
+        is a blocking host-to-device copy)."""
+        k = (ref.device, ref.dtype)
+        t = self._iden6.get(k)
+        if t is None:
+            t = torch.tensor(_IDEN6, device=ref.device, dtype=ref.dtype)
+            self._iden6[k] = t
+        return t
 
     def _dist_loss(self, feat1, feat2, dist1, dist2):
         numbers1 = random.sample(range(dist1.shape[1]), self.N_dist)      # same host-RNG draw order as :1361-1364
@@ -129,7 +150,7 @@ class _GraphDeformBase(nn.Module):
             deformations = deformer.forward_fused(feat1, feat2, idx11, idx22, verts1, verts12, Pi_12, fps1)
         else:                                   # a foreign Deformer: the reference's call, gathers materialised
             deformations = deformer(index_points(feat1, idx11), index_points(feat2, idx22), verts1, verts12, Pi_12, fps1)
-        rotations = deformations[:, :, 3:] + torch.tensor(_IDEN6, device=deformations.device, dtype=deformations.dtype)
+        rotations = deformations[:, :, 3:] + self._identity6(deformations)
         T1 = deformations[:, :, :3]
         R1 = rotation_6d_to_matrix(rotations)
         deformed_points1, arap, _sr = deform_batched(verts1, graph, R1, T1)
@@ -174,6 +195,7 @@ class GraphDeformLoss_Neural(_GraphDeformBase):
             loss += self.dist_loss
         B, N, _ = verts1.shape
         k = self.k_deform
+        self._graph_slot = 0
         num_nodes_all1, dg1 = self.deformation_graph_node(verts1)
         num_nodes_all2, dg2 = self.deformation_graph_node(verts2)
         Pi_12 = self.topk_pi(maps.knnsearch_t_grad(feat1, feat2, alpha=alpha_i))
@@ -223,6 +245,7 @@ class GraphDeformLoss_Neural_Partial(_GraphDeformBase):
         self_rec12 = self_rec21 = None
         if self.w_deform > 0:
             k = self.k_deform
+            self._graph_slot = 0
             num_nodes_all1, dg1 = self.deformation_graph_node(verts1)
             num_nodes_all2, dg2 = self.deformation_graph_node(verts2)
             Pi_12 = self.topk_pi(maps.knnsearch_t_grad(feat1, feat2, alpha=alpha_i))

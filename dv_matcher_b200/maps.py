@@ -115,6 +115,10 @@ class SparseSoftMap(_MapBase):
     """Top-k soft map: idx int32 [B,N,k] (ascending distance), w fp32 [B,N,k], logical shape [B,N,M]."""
 
     def __init__(self, idx, w, M, argmin=None, top_d=None, row_min=None, row_sum=None):
+        if idx.dtype != torch.int32:
+            idx = idx.to(torch.int32)
+        if w.dtype != torch.float32:                      # the kernels read float32 weights: never reinterpret another dtype
+            w = w.float()
         self.idx, self.w, self.M = idx, w, int(M)
         self.argmin, self.top_d, self.row_min, self.row_sum = argmin, top_d, row_min, row_sum
         self.shape = torch.Size((idx.shape[0], idx.shape[1], self.M))

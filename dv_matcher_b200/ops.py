@@ -79,7 +79,7 @@ def sparse_transfer_fwd(idx, w, y):
     B, N, K = idx.shape
     M, D = y.shape[1], y.shape[2]
     out = torch.empty(B, N, D, dtype=torch.float32, device=y.device)
-    check(lib.dvm_sparse_transfer_fwd(ptr(idx), ptr(w), ptr(y), B, N, M, K, D, ptr(out), stream_ptr()), "dvm_sparse_transfer_fwd")
+    check(lib.dvm_sparse_transfer_fwd(ptr(idx, torch.int32), ptr(w, torch.float32), ptr(y), B, N, M, K, D, ptr(out), stream_ptr()), "dvm_sparse_transfer_fwd")
     return out
 
 
@@ -90,7 +90,7 @@ def sparse_transfer_bwd(idx, w, y, d_out, need_dw=True, need_dy=True):
     M, D = y.shape[1], y.shape[2]
     dw = torch.empty(B, N, K, dtype=torch.float32, device=y.device) if need_dw else None
     dy = torch.zeros_like(y) if need_dy else None
-    check(lib.dvm_sparse_transfer_bwd(ptr(idx), ptr(w), ptr(y), ptr(d_out), B, N, M, K, D, ptr(dw), ptr(dy), stream_ptr()),
+    check(lib.dvm_sparse_transfer_bwd(ptr(idx, torch.int32), ptr(w, torch.float32), ptr(y), ptr(d_out), B, N, M, K, D, ptr(dw), ptr(dy), stream_ptr()),
           "dvm_sparse_transfer_bwd")
     return dw, dy
 
@@ -247,6 +247,69 @@ def arap_bwd(xyz, nodes_idx, ring, R, t, g_arap, dR, dt):
     check(lib.dvm_arap_bwd(ptr(xyz), ptr(nodes_idx), ptr(ring), ptr(R), ptr(t), ptr(g_arap), B, N, K, rk, ptr(dR), ptr(dt), stream_ptr()),
           "dvm_arap_bwd")
     return dR, dt
+
+
+def node_table(R, t, nodes_xyz):
+    """Pack (R [B,K,3,3], t [B,K,3], g [B,K,3]) into 64-byte node records [B,K,16] (dvm_node_table)."""
+    lib = _lib.load()
+    R, t, nodes_xyz = f32c(R), f32c(t), f32c(nodes_xyz)
+    require_device(R)
+    B, K = nodes_xyz.shape[0], nodes_xyz.shape[1]
+    table = torch.empty(B, K, 16, dtype=torch.float32, device=R.device)
+    check(lib.dvm_node_table(ptr(R), ptr(t), ptr(nodes_xyz), B, K, ptr(table), stream_ptr()), "dvm_node_table")
+    return table
+
+
+def node_table_from_d9(d9, nodes_xyz, want_rt=False):
+    """Deformer output d9 [B,K,9] -> node records (identity offset + 6D -> R fused; dvm_node_table_from_d9).
+    Returns table or (table, R [B,K,3,3], t [B,K,3])."""
+    lib = _lib.load()
+    d9, nodes_xyz = f32c(d9), f32c(nodes_xyz)
+    require_device(d9)
+    B, K = nodes_xyz.shape[0], nodes_xyz.shape[1]
+    table = torch.empty(B, K, 16, dtype=torch.float32, device=d9.device)
+    R = torch.empty(B, K, 3, 3, dtype=torch.float32, device=d9.device) if want_rt else None
+    t = torch.empty(B, K, 3, dtype=torch.float32, device=d9.device) if want_rt else None
+    check(lib.dvm_node_table_from_d9(ptr(d9), ptr(nodes_xyz), B, K, ptr(table), ptr(R), ptr(t), stream_ptr()), "dvm_node_table_from_d9")
+    return (table, R, t) if want_rt else table
+
+
+def skin_fwd_packed(xyz, pack, table):
+    """Skinning warp on the packed graph layout (dvm_skin_fwd_packed). pack: deformation_graph.GraphPack."""
+    lib = _lib.load()
+    xyz = f32c(xyz)
+    require_device(xyz)
+    B, N, _ = xyz.shape
+    K = table.shape[1]
+    out = torch.empty_like(xyz)
+    check(lib.dvm_skin_fwd_packed(ptr(xyz), ptr(pack.vorder, torch.int32), ptr(pack.s_infl, torch.int32), ptr(pack.s_w, torch.float32),
+                                  ptr(table, torch.float32), B, N, K, ptr(out), stream_ptr()), "dvm_skin_fwd_packed")
+    return out
+
+
+def skin_bwd_csr(xyz, pack, d_out):
+    lib = _lib.load()
+    xyz, d_out = f32c(xyz), f32c(d_out)
+    B, N, _ = xyz.shape
+    K = pack.nodes_xyz.shape[1]
+    dR = torch.empty(B, K, 3, 3, dtype=torch.float32, device=xyz.device)
+    dt = torch.empty(B, K, 3, dtype=torch.float32, device=xyz.device)
+    check(lib.dvm_skin_bwd_csr(ptr(xyz), ptr(pack.nodes_xyz, torch.float32), ptr(pack.csr_ptr, torch.int32), ptr(pack.csr_vert, torch.int32),
+                               ptr(pack.csr_w, torch.float32), ptr(d_out), B, N, K, ptr(dR), ptr(dt), stream_ptr()), "dvm_skin_bwd_csr")
+    return dR, dt
+
+
+def arap_fwd_packed(pack, table, want_sr=True):
+    lib = _lib.load()
+    require_device(table)
+    B, K = table.shape[0], table.shape[1]
+    rk = pack.s_ring.shape[1]
+    arap = torch.empty(B, dtype=torch.float32, device=table.device)
+    sr = torch.empty(B, dtype=torch.float32, device=table.device) if want_sr else None
+    ws = _lib.workspace.get(lib.dvm_arap_packed_workspace_bytes(B, K), table.device, "arap")
+    check(lib.dvm_arap_fwd_packed(ptr(pack.norder, torch.int32), ptr(pack.s_ring, torch.int32), ptr(table, torch.float32), B, K, rk,
+                                  ptr(arap), ptr(sr), ptr(ws), ws.numel(), stream_ptr()), "dvm_arap_fwd_packed")
+    return arap, sr
 
 
 def gather_conv_fwd(feat, idx, weight, bias):

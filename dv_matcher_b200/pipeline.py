@@ -2,43 +2,36 @@
 
 match : Pi_12, Pi_21 (top-10 idx + w), verts12 = Pi_12 @ verts2, verts21, hard maps T12, T21
         -> ONE batched dvm_softmap_fwd over the 2B (source, target) problems (both directions).
-deform: xyz 10-NN of every cloud, Deformer (torch MLP; gathers fused), 6D -> R, skinning + ARAP,
+deform: xyz 10-NN of every cloud, Deformer (gathers fused, decoder MLP on tcgen05), 6D -> R, skinning + ARAP,
         Chamfer(deformed, target) and Chamfer(verts12, verts2), both directions
         -> the orchestration of GraphDeformLoss_Neural.deform (models/loss.py:1228-1282) / deform.py:229-257
            without the prints, OFF dumps and Python per-batch-element loops.
 Graphs are built once per shape (`build_graphs`) and passed in ("warm"); `build_graphs` timed alone is
 the "cold" cost the reference pays on the CPU every step (models/loss.py:1401-1402).
+
+`MatchDeformEngine` is the end-to-end form: pinned host buffers in, pinned host results out, the warm step replayed
+as ONE CUDA graph launch (no per-kernel host work, so the slowest rank of a multi-GPU job is not decided by host
+jitter), H2D / compute / D2H of consecutive steps overlapped on three streams.
 """
 import torch
 
 from . import maps, ops
-from .deformation_graph import BatchedGraph, build_graphs, deform_batched
-from .geometry import rotation_6d_to_matrix
-
-_IDEN6 = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0)
-_IDEN6_DEV = {}
+from .deformation_graph import BatchedGraph, build_graphs, deform_from_d9
 
 
-def _iden6(device):
-    """The identity offset of models/loss.py:1259-1262 as a cached device constant: building it per step from a Python
-    list is a blocking host-to-device copy, i.e. a full stream synchronisation in the middle of every step."""
-    t = _IDEN6_DEV.get(device)
-    if t is None:
-        t = torch.tensor(_IDEN6, device=device, dtype=torch.float32)
-        _IDEN6_DEV[device] = t
-    return t
+# what a step produces (deform.py:242-262 writes `deformed`; test.py:110-121 writes T; the losses read the rest)
+RESULT_NAMES = ("T", "top_idx", "top_w", "verts_t", "deformed", "arap", "cd_deform", "cd_self")
 
 
 def cat_graphs(g1, g2):
-    return BatchedGraph(*[torch.cat([a, b]) for a, b in zip(
-        (g1.nodes_idx, g1.influence, g1.dists, g1.weights, g1.ring, g1.sigma),
-        (g2.nodes_idx, g2.influence, g2.dists, g2.weights, g2.ring, g2.sigma))])
+    return BatchedGraph.cat([g1, g2])
 
 
 def match(feat1, feat2, verts1, verts2, alpha=100.0, prec=None):
-    """Both directions of the fused soft/hard map for B pairs with N == M (one launch sequence).
+    """Both directions of the fused soft/hard map for B pairs (one launch sequence when N == M).
 
-    Returns (SparseSoftMap over the 2B stacked problems [12-direction first], verts_transferred [2B,N,3])."""
+    N == M : returns (SparseSoftMap over the 2B stacked problems [12-direction first], verts_transferred [2B,N,3]).
+    N != M (partial-to-full, config 2): returns ((sm12, sm21), (verts12 [B,N,3], verts21 [B,M,3]))."""
     if feat1.shape[1] == feat2.shape[1]:
         X = torch.cat([feat1, feat2])
         Y = torch.cat([feat2, feat1])
@@ -49,115 +42,207 @@ def match(feat1, feat2, verts1, verts2, alpha=100.0, prec=None):
     return (sm12, sm21), (v12, v21)
 
 
-def match_deform(feat1, feat2, verts1, verts2, graphs, deformer, alpha=100.0, k_deform=10, prec=None):
-    """One pass of the hot path over B pairs (N == M).  `graphs` = BatchedGraph over cat([verts1, verts2]).
-
-    Returns a dict of device tensors; nothing is synchronised or copied to the host here."""
-    B, N, _ = verts1.shape
-    src = torch.cat([verts1, verts2])                                      # source cloud of each of the 2B problems
-    tgt = torch.cat([verts2, verts1])
-    fsrc = torch.cat([feat1, feat2])
-    ftgt = torch.cat([feat2, feat1])
+def match_deform_stacked(fsrc, ftgt, src, tgt, graphs, deformer, alpha=100.0, k_deform=10, prec=None):
+    """match + deform over P = 2B stacked (source, target) problems: problem p < B is pair p in direction 1->2,
+    problem B + p the same pair in direction 2->1 (so tgt == roll(src, B) and idx of the target cloud is a roll too).
+    `graphs` = BatchedGraph over `src`.  Nothing is synchronised or copied to the host here."""
+    P = src.shape[0]
+    B = P // 2
     sm, vt = maps.soft_map(fsrc, ftgt, alpha, v=tgt, prec=prec)            # [2B,...]: rows 0..B-1 = 1->2, B..2B-1 = 2->1
     idx_self = ops.knn3(src, src, k_deform)                                # idx11 | idx22  (models/loss.py:1229-1230)
     idx_tgt = torch.cat([idx_self[B:], idx_self[:B]])
     fps = graphs.nodes_idx
     deformations = deformer.forward_fused(fsrc, ftgt, idx_self, idx_tgt, src, vt, sm, fps)     # [2B,K,9]
-    iden = _iden6(src.device)
-    R = rotation_6d_to_matrix(deformations[..., 3:] + iden)               # models/loss.py:1258-1264
-    T = deformations[..., :3].contiguous()
-    deformed, arap, sr = deform_batched(src, graphs, R, T)                 # models/loss.py:1269-1273
+    # identity offset + 6D -> R (models/loss.py:1258-1264) + skinning + ARAP (:1269-1273); the smoothness term is never used
+    deformed, arap, _ = deform_from_d9(src, graphs, deformations)
     cd_d1, cd_d2, _, _ = ops.chamfer_fwd(deformed, tgt)                    # chamfer(deformed, target)   :1279
     cd_s1, cd_s2, _, _ = ops.chamfer_fwd(vt, tgt)                          # chamfer(verts12, verts2)    :1280
     return dict(T=sm.argmin, top_idx=sm.idx, top_w=sm.w, verts_t=vt, deformed=deformed, arap=arap,
-                cd_deform=cd_d1.mean(1) + cd_d2.mean(1), cd_self=cd_s1.mean(1) + cd_s2.mean(1))
+                cd_deform=cd_d1.mean(1) + cd_d2.mean(1), cd_self=cd_s1.mean(1) + cd_s2.mean(1),
+                deformations=deformations, knn_self=idx_self)
+
+
+def match_deform(feat1, feat2, verts1, verts2, graphs, deformer, alpha=100.0, k_deform=10, prec=None):
+    """One pass of the hot path over B pairs (N == M).  `graphs` = BatchedGraph over cat([verts1, verts2]).
+
+    Returns a dict of device tensors over the 2B problems; nothing is synchronised or copied to the host here."""
+    src = torch.cat([verts1, verts2])                                      # source cloud of each of the 2B problems
+    tgt = torch.cat([verts2, verts1])
+    fsrc = torch.cat([feat1, feat2])
+    ftgt = torch.cat([feat2, feat1])
+    return match_deform_stacked(fsrc, ftgt, src, tgt, graphs, deformer, alpha, k_deform, prec)
+
+
+class _Slot:
+    """One of the engine's two in-flight steps: static device inputs, the captured CUDA graph that reads them, its
+    static outputs, pinned host outputs and the events that order H2D -> compute -> D2H."""
+
+    def __init__(self):
+        self.shape = None
+        self.fsrc = self.src = None
+        self.graphs = None                 # static BatchedGraph buffers the captured step reads
+        self.graph_key = object()          # key of the graph tensors currently in `graphs` (sentinel: none)
+        self.cuda_graph = None
+        self.out = None                    # device outputs (static once captured)
+        self.host = {}
+        self.h2d_done = torch.cuda.Event()
+        self.compute_done = torch.cuda.Event()
+        self.d2h_done = torch.cuda.Event()
+        self.busy = False
+        self.warm = 0
 
 
 class MatchDeformEngine:
-    """Public end-to-end entry: host (pinned) buffers in, host results out, on the current device.
+    """Public end-to-end entry: pinned host buffers in, pinned host results out, on one device.
 
-    step(feat1, feat2, verts1, verts2) copies the step's inputs H2D, runs match_deform and reads the step's
-    results back (hard maps T12/T21 int64 [2B,N] and the per-problem losses) -- the call bench.py's `e2e`
-    number times.  Staging buffers are double-buffered: `prefetch(...)` (or step(..., next_inputs=...)) starts the
-    H2D copy of the NEXT step's inputs on a copy stream while the current step computes, so the PCIe transfer of
-    step i+1 overlaps the kernels of step i; every step's inputs are still copied inside that step's call sequence.
-    """
+        t = eng.submit(feat1, feat2, verts1, verts2, graph_key=...)     # asynchronous: H2D, compute, D2H are enqueued
+        res = eng.result(t)                                             # waits for THAT step's D2H; dict of pinned tensors
 
-    def __init__(self, deformer, alpha=100.0, k_deform=10, prec=None, device=None):
+    `step(...)` = `result(submit(...))`.  Two steps can be in flight: submitting step i+1 before asking for the result of
+    step i overlaps its H2D copy (copy-in stream) with the kernels of step i and the D2H of step i (copy-out stream)
+    with the kernels of step i+1.  Every step's inputs and results cross PCIe inside its own submit/result pair.
+    The warm step (same shapes as the previous use of the slot) is one CUDA-graph launch.
+
+    Deformation graphs: `graph_key=None` (default) rebuilds them from the step's own vertices (the reference's
+    behaviour, models/loss.py:1401-1402); a hashable key opts into the per-shape cache -- the caller promises that
+    equal keys mean equal clouds, the cache only checks (B, N)."""
+
+    def __init__(self, deformer, alpha=100.0, k_deform=10, prec=None, device=None, use_cuda_graph=True, max_cached_graphs=64):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.deformer = deformer.to(self.device).eval()
         self.alpha, self.k_deform, self.prec = alpha, k_deform, prec
-        self._dev = [{}, {}]            # two staging sets
-        self._slot = 0
-        self._pending = None            # (slot, event, host tensors identity) of a prefetched batch
-        self._copy_stream = torch.cuda.Stream(self.device)
-        self._host_out = {}
+        self.use_cuda_graph = use_cuda_graph
+        self._slots = [_Slot(), _Slot()]
+        self._next = 0
+        self._in_stream = torch.cuda.Stream(self.device)
+        self._out_stream = torch.cuda.Stream(self.device)
+        self._compute_stream = torch.cuda.Stream(self.device)
         self._graph_cache = {}
+        self._max_cached = max_cached_graphs
+        self._pool = None
+        self.launch_mode = "eager"
 
-    def _stage(self, slot, name, host, stream):
-        buf = self._dev[slot].get(name)
-        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
-            buf = torch.empty(host.shape, dtype=host.dtype, device=self.device)
-            self._dev[slot][name] = buf
-        with torch.cuda.stream(stream):
-            buf.copy_(host, non_blocking=True)
-        return buf
-
-    def _copy_in(self, slot, inputs, stream):
-        names = ("f1", "f2", "v1", "v2")
-        bufs = [self._stage(slot, n, h, stream) for n, h in zip(names, inputs)]
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        return bufs, ev
-
-    def prefetch(self, feat1, feat2, verts1, verts2):
-        """Start the H2D copy of the next step's inputs (pinned host tensors) on the copy stream."""
-        slot = 1 - self._slot
-        # the staging set may still be read by kernels of the step before last: order the copy after the compute stream
-        self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
-        bufs, ev = self._copy_in(slot, (feat1, feat2, verts1, verts2), self._copy_stream)
-        self._pending = (slot, ev, bufs, tuple(id(t) for t in (feat1, feat2, verts1, verts2)))
-
+    # ---- deformation-graph cache ("warm" path)
     def graphs_for(self, key, verts_cat, start=None):
-        """Per-shape graph cache ("warm" path). key identifies the batch of shapes."""
         g = self._graph_cache.get(key)
+        if g is not None and tuple(g.influence.shape[:2]) != tuple(verts_cat.shape[:2]):
+            raise RuntimeError(f"graph_key {key!r} was built for clouds of shape {tuple(g.influence.shape[:2])}, "
+                               f"this step has {tuple(verts_cat.shape[:2])}: keys must identify the shapes")
         if g is None:
             g = build_graphs(verts_cat, start)
+            if len(self._graph_cache) >= self._max_cached:
+                self._graph_cache.pop(next(iter(self._graph_cache)))
             self._graph_cache[key] = g
         return g
 
+    def put_graphs(self, key, graphs):
+        self._graph_cache[key] = graphs
+
+    # ---- one step
+    def _ensure_inputs(self, s, B, N, C):
+        shape = (B, N, C)
+        if s.shape != shape:
+            with torch.cuda.stream(self._compute_stream):
+                s.fsrc = torch.empty(2 * B, N, C, dtype=torch.float32, device=self.device)
+                s.src = torch.empty(2 * B, N, 3, dtype=torch.float32, device=self.device)
+            s.shape, s.cuda_graph, s.graphs, s.out, s.host = shape, None, None, None, {}
+            s.graph_key = object()
+            s.warm = 0
+
+    def _run(self, s):
+        B = s.shape[0]
+        ftgt = torch.cat([s.fsrc[B:], s.fsrc[:B]])
+        tgt = torch.cat([s.src[B:], s.src[:B]])
+        out = match_deform_stacked(s.fsrc, ftgt, s.src, tgt, s.graphs, self.deformer, self.alpha, self.k_deform, self.prec)
+        return {k: out[k] for k in RESULT_NAMES}
+
     @torch.no_grad()
-    def step(self, feat1, feat2, verts1, verts2, graph_key="default", fps_start=None, next_inputs=None):
-        cur = torch.cuda.current_stream(self.device)
-        ids = tuple(id(t) for t in (feat1, feat2, verts1, verts2))
-        if self._pending is not None and self._pending[3] == ids:           # inputs already on their way
-            slot, ev, bufs, _ = self._pending
-            cur.wait_event(ev)
-        else:
-            slot = 1 - self._slot
-            bufs, ev = self._copy_in(slot, (feat1, feat2, verts1, verts2), cur)
-        self._pending = None
-        self._slot = slot
-        f1, f2, v1, v2 = bufs
-        graphs = self.graphs_for(graph_key, torch.cat([v1, v2]), fps_start)
-        if next_inputs is not None:
-            self.prefetch(*next_inputs)                                     # overlaps with the kernels launched below
-        out = match_deform(f1, f2, v1, v2, graphs, self.deformer, self.alpha, self.k_deform, self.prec)
-        res = {}
-        for name in ("T", "cd_deform", "cd_self", "arap"):
-            t = out[name]
-            h = self._host_out.get(name)
-            if h is None or h.shape != t.shape:
-                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                self._host_out[name] = h
-            h.copy_(t, non_blocking=True)
-            res[name] = h
-        cur.synchronize()
-        return res
+    def submit(self, feat1, feat2, verts1, verts2, graph_key=None, fps_start=None):
+        for t in (feat1, feat2, verts1, verts2):
+            if t.is_cuda:
+                raise RuntimeError("MatchDeformEngine.submit takes HOST tensors (pinned for asynchronous copies)")
+        B, N, C = feat1.shape
+        if feat2.shape != feat1.shape or verts1.shape != (B, N, 3) or verts2.shape != (B, N, 3):
+            raise RuntimeError("MatchDeformEngine: N == M pairs only; use pipeline.match for partial pairs")
+        s = self._slots[self._next]
+        self._next ^= 1
+        if s.busy:                                       # the slot's previous results were never collected
+            s.d2h_done.synchronize()
+            s.busy = False
+        self._ensure_inputs(s, B, N, C)
+        cin, cmp, cout = self._in_stream, self._compute_stream, self._out_stream
+        # H2D: the slot's previous step has released its inputs once its D2H has been issued after compute_done
+        cin.wait_event(s.compute_done)
+        with torch.cuda.stream(cin):
+            s.fsrc[:B].copy_(feat1, non_blocking=True)
+            s.fsrc[B:].copy_(feat2, non_blocking=True)
+            s.src[:B].copy_(verts1, non_blocking=True)
+            s.src[B:].copy_(verts2, non_blocking=True)
+            s.h2d_done.record(cin)
+        cmp.wait_event(s.h2d_done)
+        cmp.wait_event(s.d2h_done)                       # static outputs of this slot are free again
+        with torch.cuda.stream(cmp):
+            if graph_key is None:
+                g = build_graphs(s.src, fps_start)
+                key = object()
+            else:
+                g = self.graphs_for(graph_key, s.src, fps_start)
+                key = graph_key
+            if s.graphs is None:
+                s.graphs = BatchedGraph.from_tensors([t.clone() for t in g.tensors()])
+                s.graph_key = key
+            elif key is not s.graph_key and key != s.graph_key:
+                for dst, srct in zip(s.graphs.tensors(), g.tensors()):
+                    dst.copy_(srct, non_blocking=True)
+                s.graph_key = key
+            if s.cuda_graph is not None:
+                s.cuda_graph.replay()
+                self.launch_mode = "cuda_graph"
+            elif self.use_cuda_graph and s.warm >= 1:
+                # second use of the slot at this shape: every lazy one-time initialisation (function attributes, workspaces,
+                # constants) happened in the eager run; capture the step.  Graph-private memory is shared by both slots.
+                from . import _lib
+                _lib.workspace.keep_retired = True           # the captured kernels hold raw workspace addresses
+                cg = torch.cuda.CUDAGraph()
+                if self._pool is None:
+                    self._pool = torch.cuda.graph_pool_handle()
+                cmp.synchronize()
+                with torch.cuda.graph(cg, pool=self._pool, stream=cmp):
+                    s.out = self._run(s)
+                s.cuda_graph = cg
+                cg.replay()
+                self.launch_mode = "cuda_graph"
+            else:
+                s.out = self._run(s)
+                s.warm += 1
+            s.compute_done.record(cmp)
+        cout.wait_event(s.compute_done)
+        with torch.cuda.stream(cout):
+            for name in RESULT_NAMES:
+                t = s.out[name]
+                h = s.host.get(name)
+                if h is None or h.shape != t.shape or h.dtype != t.dtype:
+                    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    s.host[name] = h
+                h.copy_(t, non_blocking=True)
+                if s.cuda_graph is None:
+                    t.record_stream(cout)
+            s.d2h_done.record(cout)
+        s.busy = True
+        return s
+
+    def result(self, ticket):
+        ticket.d2h_done.synchronize()
+        ticket.busy = False
+        return ticket.host
+
+    def step(self, feat1, feat2, verts1, verts2, graph_key=None, fps_start=None):
+        return self.result(self.submit(feat1, feat2, verts1, verts2, graph_key, fps_start))
 
     @staticmethod
     def h2d_bytes(feat1, feat2, verts1, verts2):
         return sum(t.numel() * t.element_size() for t in (feat1, feat2, verts1, verts2))
 
     def d2h_bytes(self):
-        return sum(t.numel() * t.element_size() for t in self._host_out.values())
+        s = self._slots[0]
+        return sum(t.numel() * t.element_size() for t in s.host.values())

@@ -52,6 +52,9 @@ long long   dvm_launch_count(void);
  * recorded events and returns the summed duration and the number of launches bracketed. */
 int         dvm_profile_enable(int on);
 int         dvm_profile_read(double* total_ms, int* brackets);
+/* same for a named channel: 0 = the candidate pass (priming + sweep), 1 = the whole fused op dvm_softmap_fwd
+ * (operand preparation + priming + sweep + finalize + rescue), the span north_star's tensor-peak target is quoted on */
+int         dvm_profile_read_channel(int channel, double* total_ms, int* brackets);
 
 /* ------------------------------------------------------------------------------------------
  * Fused similarity -> row softmax -> top-k soft map -> Pi.V -> arg-min, never materialising N x M.
@@ -157,6 +160,29 @@ int dvm_arap_fwd(const float* xyz, const int64_t* nodes_idx, const int64_t* ring
                  int B, int N, int K, int ring_k, float* arap, float* sr, void* ws, size_t ws_bytes, void* stream);
 int dvm_arap_bwd(const float* xyz, const int64_t* nodes_idx, const int64_t* ring, const float* R, const float* t,
                  const float* g_arap, int B, int N, int K, int ring_k, float* dR, float* dt, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-shaped layout of the same forward (lib/deformation_graph_point.py:233-261): the product path.  The graph is
+ * static per shape, so the host lays it out once (deformation_graph.build_graphs):
+ *   table   f32[B][K][16]   node records, 64-byte aligned: R0..R8, t0..t2, g0..g2, 0   (g = xyz[nodes_idx])
+ *   vorder  int32[B][N]     vertices in Morton order;  s_infl int32[B][3][N], s_w f32[B][3][N]: influence lists of
+ *                           vertex vorder[i], slot-major;  norder int32[B][K], s_ring int32[B][ring_k][K]: same for the ring;
+ *   csr_ptr int32[B][K+1], csr_vert int32[B][3N], csr_w f32[B][3N]: vertices influenced by each node (ascending vertex id).
+ * dvm_node_table packs (R, t, g); dvm_node_table_from_d9 fuses models/loss.py:1257-1264 + rotation_6d_to_matrix (39-45):
+ *   d9[B][K][9] = Deformer output, t = d9[0:3], R = rot6d(d9[3:9] + [1,0,0,0,1,0]); R_out/t_out optional plain copies.
+ * dvm_skin_fwd_packed == dvm_skin_fwd, dvm_arap_fwd_packed == dvm_arap_fwd (sr may be NULL: smoothness skipped),
+ * dvm_skin_bwd_csr == dvm_skin_bwd without atomics (deterministic; dR, dt OVERWRITTEN).
+ * ------------------------------------------------------------------------------------------ */
+int dvm_node_table(const float* R, const float* t, const float* nodes_xyz, int B, int K, float* table, void* stream);
+int dvm_node_table_from_d9(const float* d9, const float* nodes_xyz, int B, int K, float* table,
+                           float* R_out, float* t_out, void* stream);
+int dvm_skin_fwd_packed(const float* xyz, const int32_t* vorder, const int32_t* s_infl, const float* s_w,
+                        const float* table, int B, int N, int K, float* out, void* stream);
+int dvm_skin_bwd_csr(const float* xyz, const float* nodes_xyz, const int32_t* csr_ptr, const int32_t* csr_vert,
+                     const float* csr_w, const float* dOut, int B, int N, int K, float* dR, float* dt, void* stream);
+size_t dvm_arap_packed_workspace_bytes(int B, int K);
+int dvm_arap_fwd_packed(const int32_t* norder, const int32_t* s_ring, const float* table, int B, int K, int ring_k,
+                        float* arap, float* sr, void* ws, size_t ws_bytes, void* stream);
 
 /* index_points + Conv2d(k->1, 1x1) over the neighbour axis, fused (models/loss.py:1252-1253 feeding
  * models/model.py:468-469):  out[b,r,c] = bias + sum_s W[s] * feat[b, idx[b,r,s], c]  for feat[B,N,C],

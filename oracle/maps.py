@@ -104,6 +104,43 @@ def softmap_sparse(x, y, alpha, k=TOPK, v=None, dtype=torch.float64, chunk=256, 
     return out
 
 
+def exact_d2_rows_blocked(x_rows, y, dtype=torch.float64, cblock=16, rblock=32):
+    """[R,M] squared direct-difference distances like `_exact_d2_rows`, accumulated over channel blocks so that the
+    temporary is [rblock, M, cblock] instead of [R, M, C] (M = 200k fits).  Same arithmetic form (sub, square, sum)."""
+    xr = x_rows.to(dtype)
+    yy = y.to(dtype)
+    R, C = xr.shape
+    out = torch.zeros(R, yy.shape[0], dtype=dtype)
+    for r0 in range(0, R, rblock):
+        acc = out[r0:r0 + rblock]
+        for c0 in range(0, C, cblock):
+            diff = xr[r0:r0 + rblock, None, c0:c0 + cblock] - yy[None, :, c0:c0 + cblock]
+            acc += (diff * diff).sum(-1)
+    return out
+
+
+def softmap_from_d2(d2, alpha, k=TOPK, v=None):
+    """Sparse soft-map quantities of `softmap_sparse` for a block of rows given their exact squared distances [R,M]
+    (one sort serves every alpha: pass a list of alphas to get a list of results)."""
+    alphas = list(alpha) if isinstance(alpha, (list, tuple)) else [alpha]
+    d = d2.clamp_min(0).sqrt()
+    ds, order = torch.sort(d, dim=-1, stable=True)
+    M = d.shape[1]
+    kk = min(k + 1, M)
+    res = []
+    for a in alphas:
+        e_all = torch.exp(-a * (ds - ds[:, :1]))
+        rs = e_all.sum(-1)
+        w = e_all[:, :k] / rs[:, None]
+        o = dict(argmin=order[:, 0].clone(), idx=order[:, :k].clone(), d=ds[:, :k].clone(), w=w, row_sum=rs,
+                 gap=(ds[:, kk - 1] - ds[:, k - 1]) if kk > k else torch.full_like(rs, float("inf")),
+                 gap1=(ds[:, 1] - ds[:, 0]) if M > 1 else torch.full_like(rs, float("inf")))
+        if v is not None:
+            o["piv"] = (w[:, :, None] * v.to(d.dtype)[order[:, :k]]).sum(1)
+        res.append(o)
+    return res if isinstance(alpha, (list, tuple)) else res[0]
+
+
 def sparse_to_dense(idx, w, M):
     """scatter(idx, w) -> dense [B,N,M]; the form parity on Pi is defined on."""
     B, N, _ = idx.shape

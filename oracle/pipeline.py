@@ -38,44 +38,58 @@ def _full_cloud_parts(feat_tgt, verts_src, verts_tgt, graph, deformer_params, k=
     """Per-cloud work that does not scale with the row slab: target-side conv gather, MLP, skinning + ARAP."""
     idx22 = og.knn_grad(verts_tgt[:, :256], verts_tgt, k)              # (slab of the target k-NN; scaled by caller)
     K = graph["nodes_idx"].shape[0]
-    x = torch.zeros(1, K, 262)
+    dev = verts_src.device
+    x = torch.zeros(1, K, 262, device=dev)
     lin = "deformation_decoder_layer.linear."
     for i in (0, 2, 4):
         x = F.elu(F.linear(x, deformer_params[f"{lin}{i}.weight"], deformer_params[f"{lin}{i}.bias"]))
     d9 = F.linear(x, deformer_params[f"{lin}6.weight"], deformer_params[f"{lin}6.bias"])
-    iden = torch.tensor([1, 0, 0, 0, 1, 0], dtype=torch.float32)
+    iden = torch.tensor([1, 0, 0, 0, 1, 0], dtype=torch.float32, device=dev)
     R = og.rotation_6d_to_matrix(d9[..., 3:] + iden)
     warped, arap, sr = ogr.dg_forward(verts_src[0], graph["nodes_idx"], graph["influence"], graph["weights"],
                                       graph["one_ring"], R, d9[..., :3])
     return idx22, warped, arap
 
 
-def time_pair_sample(batch, graph, deformer_params, alpha=100.0, rows=2048, repeats=1):
-    """Seconds the reference's CPU op sequence needs for ONE pair (both directions), extrapolated from a
-    slab of `rows` source rows per direction.  batch: dict of [1,N,*] CPU tensors (one pair)."""
+def time_pair_sample(batch, graph, deformer_params, alpha=100.0, rows=2048, repeats=1, sync=None, results=None):
+    """Seconds the reference's op sequence needs for ONE pair (both directions), extrapolated from a slab of `rows` source
+    rows per direction (rows >= N: the full, un-extrapolated sequence).  batch: dict of [1,N,*] tensors (one pair) on the
+    device to time (CPU = the reference's own CPU path; CUDA = "stock PyTorch on the same B200") -- `sync` is
+    called before every clock read (torch.cuda.synchronize for CUDA tensors).  `results`, if a dict, receives the first
+    direction's slab outputs (t12, verts_t, rows) and the raw wall time of the sample (sample_s) for parity reporting."""
     f1, f2, v1, v2 = batch["feat1"], batch["feat2"], batch["xyz1"], batch["xyz2"]
     N, M = f1.shape[1], f2.shape[1]
-    r1 = torch.arange(min(rows, N))
-    r2 = torch.arange(min(rows, M))
+    dev = f1.device
+    r1 = torch.arange(min(rows, N), device=dev)
+    r2 = torch.arange(min(rows, M), device=dev)
+    sync = sync or (lambda: None)
     best = float("inf")
     for _ in range(repeats):
+        sync()
         t0 = time.perf_counter()
         with torch.no_grad():
-            _slab_direction(f1, f2, v1, v2, r1, alpha, deformer_params)
+            d12 = _slab_direction(f1, f2, v1, v2, r1, alpha, deformer_params)
+            sync()
             t1 = time.perf_counter()
             _slab_direction(f2, f1, v2, v1, r2, alpha, deformer_params)
+            sync()
             t2 = time.perf_counter()
             _full_cloud_parts(f2, v1, v2, graph, deformer_params)
             _full_cloud_parts(f1, v2, v1, graph, deformer_params)
+            sync()
             t3 = time.perf_counter()
         est = (t1 - t0) * (N / len(r1)) + (t2 - t1) * (M / len(r2)) + (t3 - t2)
-        best = min(best, est)
+        if est < best:
+            best = est
+            if results is not None:
+                results.update(t12=d12["t12"], verts_t=d12["verts_t"], rows=r1, sample_s=t3 - t0)
     return best
 
 
 def make_cpu_graph(verts, start=0, max_nodes=None):
     """Small real graph for the per-cloud parts (node selection itself is excluded from the timing)."""
     n = verts.shape[0]
+    verts = verts.cpu()
     if n > 6000:           # FPS on the CPU oracle is O(N^2): build the timing graph from strided nodes instead
         K = n // 2
         nodes = torch.arange(0, n, 2)[:K]
