@@ -15,9 +15,13 @@
 // (0.5-1 instruction per entry) decides whether any entry of the chunk can matter (a top-16 candidate or a
 // term inside the softmax window); only those chunks take the slow path.
 //
-// Warp roles (832 threads per CTA): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer, one lane, leader CTA),
-// warps 2..17 = scanners: TMEM lane quarter = warp % 4 (hardware rule), column group = (warp - 2) / 4: one thread = one
-// row x 64 columns of every tile; warps 18..25 = consumers (32 rows x column half of the tile each).
+// Warp roles (896 threads per CTA = 7 warpgroups): warpgroup 0 = warp 0 TMA producer, warp 1 TMEM owner (+ MMA issuer, one lane,
+// leader CTA), warps 2-3 idle; warpgroups 1-4 (warps 4..19) = scanners: TMEM lane quarter = warp % 4 (hardware rule), column
+// group = (warp - 4) / 4: one thread = one row x 64 columns of every tile; warpgroups 5-6 (warps 20..27) = consumers (32 rows x
+// column half of the tile each).  Registers are redistributed after the prologue (setmaxnreg): warpgroup 0 keeps 40, the
+// consumers 56, the scanners take 88 -- enough to pull their whole 64-column slice of the accumulator into registers with four
+// tcgen05.ld in flight and hand the TMEM stage back BEFORE any data-dependent work (min-trees, queue pushes, ring-full waits).
+// The MMA of tile t+2 therefore never waits for the slowest scanner's push path, only for the TMEM read of tile t.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> scanners), all mbarriers, signalled across the
 // pair by multicast commits / remote arrives; no CTA-wide barrier inside the sweep.
 #include <cuda.h>
@@ -34,7 +38,9 @@ constexpr int TC_KBLK = 64;           // 16-bit elements per 128-byte swizzle ro
 constexpr int TC_KEXT = 16;           // extra K block: norm columns (one UMMA K step), 32-byte swizzle rows
 constexpr int TC_SCAN_WARPS = 16;      // epilogue scanners
 constexpr int TC_CONS_WARPS = 8;       // epilogue consumers (one per 32 rows x column half of the tile)
-constexpr int TC_THREADS = 64 + 32 * (TC_SCAN_WARPS + TC_CONS_WARPS);
+constexpr int TC_LEAD_WARPS = 4;       // warpgroup 0: TMA producer, MMA issuer, two idle warps (setmaxnreg works on whole warpgroups)
+constexpr int TC_THREADS = 32 * (TC_LEAD_WARPS + TC_SCAN_WARPS + TC_CONS_WARPS);     // 896 = 7 warpgroups
+constexpr int TC_REGS_LEAD = 40, TC_REGS_SCAN = 88, TC_REGS_CONS = 56;              // 128*40 + 512*88 + 256*56 = 64512 = 72*896 (the launch allocation)
 constexpr int TC_NST = 3;             // Y ring depth
 constexpr int TC_BLK_BYTES = 128 * 128;        // one 128-row x 64-element K block
 constexpr int TC_EXT_BYTES = 128 * 32;         // one 128-row x 16-element K block
@@ -356,7 +362,11 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp == 0) {
+    // register redistribution: every role branch starts with the setmaxnreg of its warpgroup (whole warpgroups execute the
+    // same instruction; ptxas allocates the code of a branch against the budget its setmaxnreg sets)
+    if (warp < TC_LEAD_WARPS) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_LEAD));
+      if (warp == 0) {
         // =============================== TMA producer (both CTAs) ===============================
         if (lane == 0) {
             if (crank == 0) mbar_arrive_expect_tx(xfull, 2 * unit);                  // the pair's X rows: 2 x 128
@@ -373,7 +383,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 tma_load_3d_pair(&tmYe, full + s, dst + p.KB * TC_BLK_BYTES, 0, col0, b);
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // =============================== MMA issuer (leader CTA only) ===============================
         // One thread of the leader issues 9 tcgen05.mma.cta_group::2 per tile (M = 256 over the pair, N = 256, K = 16
         // each): every CTA feeds its own 128 rows of A and its own 128 columns of B from shared memory -- 8 KB per
@@ -414,10 +424,12 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 tc_commit_pair(tfull + acc);               // accumulators ready for the scanners of both CTAs
             }
         }
-    } else if (warp < 2 + TC_SCAN_WARPS) {
+      }   // warps 2, 3: nothing to do (they only hold the place of a whole warpgroup for setmaxnreg)
+    } else if (warp < TC_LEAD_WARPS + TC_SCAN_WARPS) {
         // =============================== scanners ===============================
-        const int ew = warp - 2;                           // 0..15
-        const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_SCAN));
+        const int ew = warp - TC_LEAD_WARPS;               // 0..15
+        const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's (TC_LEAD_WARPS % 4 == 0)
         const int cgp = ew >> 2;                           // column group: columns cgp*64 .. +63 of each 256-column tile
         const int ch = cgp >> 1;                           // column half: the list / consumer this warp feeds
         const int cq = ch * 4 + quarter;                   // consumer / queue of this warp's (rows, column half)
@@ -439,24 +451,26 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             mbar_wait_backoff(tfull + acc, aph);
             tc_fence_after();
             const uint32_t taddr = t_lane + acc * TC_BN;
-            // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
-            float ka[TC_CHUNK], kb[TC_CHUNK];
-            tc_ld16_issue(taddr, ka);
-            tc_ld16_wait(ka);
-            tc_ld16_issue(taddr + TC_CHUNK, kb);
-            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-            tc_ld16_wait(kb);
-            tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
-            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-            tc_ld16_wait(ka);
-            tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
-            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-            tc_ld16_wait(kb);
-            tc_fence_before();                               // all of this tile is in registers: hand the stage back
+            // the whole 64-column slice of this thread's row: four TMEM loads in flight, one wait, stage handed back at once
+            float k0[TC_CHUNK], k1[TC_CHUNK], k2[TC_CHUNK], k3[TC_CHUNK];
+            tc_ld16_issue(taddr, k0);
+            tc_ld16_issue(taddr + TC_CHUNK, k1);
+            tc_ld16_issue(taddr + 2 * TC_CHUNK, k2);
+            tc_ld16_issue(taddr + 3 * TC_CHUNK, k3);
+            tc_ld16_wait(k0);
+            tc_ld16_after_wait(k1); tc_ld16_after_wait(k2); tc_ld16_after_wait(k3);
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty + acc);
-            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-            if (q_pub != q_tail) { ring_publish(head_a + 8, q_tail, lane); q_pub = q_tail; }     // once per tile
+            if (kPrime) {
+                prime_chunk(k0, pl); prime_chunk(k1, pl); prime_chunk(k2, pl); prime_chunk(k3, pl);
+            } else {
+                scan_chunk<!kSoft>(k0, col0, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
+                scan_chunk<!kSoft>(k1, col0 + TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
+                scan_chunk<!kSoft>(k2, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
+                scan_chunk<!kSoft>(k3, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
+                if (q_pub != q_tail) { ring_publish(head_a + 8, q_tail, lane); q_pub = q_tail; }     // once per tile
+            }
         }
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
             float2* L = lists + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
@@ -470,11 +484,12 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
     } else {
         // =============================== consumers ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CONS));
         // Row lists are UNSORTED K-slot sets in shared memory; every stored key carries its slot number in its 4 low
         // mantissa bits, so "the worst entry and where it sits" is one max-tree.  Entry keys get their column offset
         // packed the same way, so "the best not yet handled key and its column" is one min-tree.  (16 ulp of
         // perturbation, covered by the certificate's E2 term; exact distances are recomputed by finalize anyway.)
-        const int cw = warp - (2 + TC_SCAN_WARPS);          // consumer index: column half * 4 + quarter
+        const int cw = warp - (TC_LEAD_WARPS + TC_SCAN_WARPS);   // consumer index: column half * 4 + quarter
         const int rl0 = cw * 32;                             // first list index li served (column half * 128 + quarter * 32); `rl` below is li
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cw * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cw * sizeof(QCtl);

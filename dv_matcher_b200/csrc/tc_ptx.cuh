@@ -121,6 +121,15 @@ __device__ __forceinline__ void tc_ld16_wait(float (&v)[16]) {
           "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
         :: "memory");
 }
+// registers of a further tcgen05.ld covered by the SAME wait: a zero-instruction barrier for the compiler, placed after
+// tc_ld16_wait -- asm volatile statements keep their order, and the in/out operands make every later use depend on it
+__device__ __forceinline__ void tc_ld16_after_wait(float (&v)[16]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(""
+        : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+          "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+        :: "memory");
+}
 // shared-memory accesses by 32-bit shared-window address (one register instead of a generic pointer pair)
 __device__ __forceinline__ void sts_v2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
 __device__ __forceinline__ float2 lds_v2(uint32_t a) { float2 r; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a) : "memory"); return r; }
