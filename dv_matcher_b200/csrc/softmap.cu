@@ -516,6 +516,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
             const float d16 = sqrtf(fmaxf(key16 - e2, 0.f));
             ok = dk < d16 - (bound + a.rel_bound * d16);
         }
+        // the 16-bit pass sums its softmax mass against a FIXED per-row reference (the priming pass' sampled minimum): a row
+        // without a finite sample, or one whose terms overflowed against it, has a non-finite mass and is settled exactly
+        if (kSoft && !(l_tot < INFINITY)) ok = false;
         if (!ok) {
             if (a.flag_list) {
                 const int e = atomicAdd(a.flag_count, 1);

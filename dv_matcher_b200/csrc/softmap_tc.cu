@@ -156,6 +156,8 @@ struct TcParams {
     int tiles_total, tiles_per_split;
     int tile_stride;             // 1 for the sweep; > 1: the priming pass visits every tile_stride-th tile only
     int multi_split;             // column-split CTAs exchange thresholds through thr_global during the sweep
+    int prime_thr;               // priming pass: also publish the list threshold (0 for small problems: the sample is too small
+                                 // for its 8th smallest chunk minimum to leave 16 candidates below it -- only the softmax reference)
     float a2, cut_over_alpha;
     uint32_t idesc;
     const float* xx;             // [B*N]
@@ -175,12 +177,19 @@ struct TcParams {
 // independent of the data.
 //
 // 8 consumer warps (one per 32 rows x column half of the tile: a row has one list per column half) drain the rings of
-// their two scanner warps with ONE LANE PER ENTRY (full lane utilisation whatever the rows are): the entry's keys below
-// the bound replace the worst entry of the row's K-entry list (shared memory) or add their softmax term
-// exp2(-a2 (d - r)) to the row's mass; the lane then publishes the row's new bound thr_hi = max(list threshold,
-// softmax-window bound).  Entries of the same row inside one batch are serialised (__match_any_sync).  Every scanner
-// warp owns a single-producer ring (tail in a register, no atomic) and publishes its entries with one fence + tail
-// store per tile; it waits for space only after publishing what it holds, the consumer never waits for a producer, so
+// their two scanner warps with ONE LANE PER ENTRY (full lane utilisation whatever the rows are).  An entry's keys are split
+// against ONE snapshot of the row's list bound `lim`:
+//   * keys >= lim can never become candidates (bounds only tighten): their softmax terms exp2(c0 - a2 d) are summed by the
+//     lane at once.  The reference of the row's mass is FIXED (c0 = a2 * r0, r0 = the priming pass' sampled row minimum), so the
+//     terms of different entries of a row are independent: same-row lanes of a batch are pre-reduced with shuffles and the
+//     first of them adds the sum to the row's accumulator -- no serialisation, however many entries a row with a wide softmax
+//     window pushes (such rows used to serialise the whole batch: up to 16 passes of the list code per batch);
+//   * keys < lim are list candidates: only these take the serialised path (same-row entries one after the other, in queue
+//     order): the key replaces the worst entry of the row's K-entry list in shared memory, what it evicts (or the key itself
+//     if the bound has tightened meanwhile) adds its term to the row's mass; the lane then publishes the row's new bound
+//     thr_hi = max(list threshold, softmax-window bound).
+// Every scanner warp owns a single-producer ring (tail in a register, no atomic) and publishes its entries with one fence +
+// tail store per tile; it waits for space only after publishing what it holds, the consumer never waits for a producer, so
 // the protocol cannot deadlock.
 //
 // The list threshold of a row starts from the PRIMING pass (8th smallest chunk minimum of a 1/10 column sample ~ rank 80) and
@@ -201,6 +210,13 @@ __device__ __forceinline__ float ex2_approx(float x) { float e; asm("ex2.approx.
 __device__ __forceinline__ float key_dist_approx(float key, float xx) {        // 2 ulp: fine for non-candidate terms
     const float x = fmaxf(fmaf(2.f, key, xx), 1e-30f);
     return x * __frsqrt_rn(x);
+}
+// d = sqrt(2 key + |x~|^2) with the MUFU reciprocal square root (2 ulp): only used for softmax terms of NON-candidate columns,
+// whose keys already carry the 16-bit operand rounding (orders of magnitude above 2 ulp)
+__device__ __forceinline__ float key_dist_fast(float key, float xx) {
+    const float x = fmaxf(fmaf(2.f, key, xx), 1e-30f);
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return x * r;
 }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float min16(const float (&k)[16]) {                  // 8 three-input min instructions
@@ -293,9 +309,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     float* thr_hi_s = reinterpret_cast<float*>(lists + TC_BM * LIST_STRIDE);           // [256] bound read by the scanners
     float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
     float* thr_mass_s = thr_list_s + TC_BM;
-    float* kr_s = thr_mass_s + TC_BM;
-    float* r_s = kr_s + TC_BM;
-    float* l_s = r_s + TC_BM;
+    float* kr_s = thr_mass_s + TC_BM;                     // smallest key seen (tightens the softmax window)
+    float* r_s = kr_s + TC_BM;                            // r0: FIXED reference distance of the row's mass (priming pass)
+    float* l_s = r_s + TC_BM;                             // sum of exp2(-a2 (d - r0)) over the non-candidate columns
     float* xx_s = l_s + TC_BM;                            // [256] |x~|^2
     float* worst_s = xx_s + TC_BM;                        // [256] largest key of the row's list (slot number in its low bits)
     QCtl* qctl = reinterpret_cast<QCtl*>(worst_s + TC_BM);   // [TC_CONS_WARPS]
@@ -338,7 +354,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             xx = __ldg(p.xx + (size_t)b * p.N + row);
             thl = kPrime ? INFINITY : 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row)) - xx);
             if (kSoft) {
-                // softmax reference from the priming pass (sample minimum >= row minimum: the window it gives is a superset)
+                // FIXED softmax reference from the priming pass (sample minimum >= row minimum: the window it gives is a
+                // superset).  A row without a finite sample keeps r = +inf: its terms become NaN and finalize sends it to
+                // the exact path.
                 const float d2s = __uint_as_float(__ldcg(p.rmin_global + (size_t)b * p.N + row));
                 thm = INFINITY;
                 if (d2s < INFINITY) {
@@ -517,36 +535,62 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const bool active = (lane & 15) < (sub ? n1 : n0);
             float k[TC_CHUNK];
             int rl = -1 - lane, cbase = 0;                            // inactive lanes: unique pseudo rows
+            float lim = -INFINITY;                                    // ONE snapshot of the row's list bound per entry
+            float mass = 0.f;
             if (active) {
                 const float4 k0 = lds_v4(ea), k1 = lds_v4(ea + 16), k2 = lds_v4(ea + 32), k3 = lds_v4(ea + 48);
                 k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
                 k[8] = k2.x; k[9] = k2.y; k[10] = k2.z; k[11] = k2.w; k[12] = k3.x; k[13] = k3.y; k[14] = k3.z; k[15] = k3.w;
                 const float2 rc = lds_v2(ea + 64);
                 rl = rl0 + __float_as_int(rc.x); cbase = __float_as_int(rc.y);
+                lim = fminf(thr_list_s[rl], worst_s[rl]);
+                if (kSoft) {
+                    // terms of the keys that can never be candidates (>= lim), inside the softmax window: fixed reference r0
+                    const float xx = xx_s[rl], thm = thr_mass_s[rl], c0 = p.a2 * r_s[rl];
 #pragma unroll
-                for (int t = 0; t < TC_CHUNK; ++t) k[t] = __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t);
+                    for (int t = 0; t < TC_CHUNK; ++t) {
+                        const float e = ex2_approx(fmaf(-p.a2, key_dist_fast(k[t], xx), c0));
+                        if (k[t] >= lim && k[t] < thm) mass += e;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < TC_CHUNK; ++t)                    // candidates keep their column offset in the 4 low bits
+                    k[t] = k[t] < lim ? __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t) : INFINITY;
             } else {
 #pragma unroll
                 for (int t = 0; t < TC_CHUNK; ++t) k[t] = INFINITY;
             }
-            // entries of the same row are processed one after the other, in queue order
             const unsigned peers = __match_any_sync(kFull, rl);
-            bool todo = active;
-            unsigned done_mask = ~__ballot_sync(kFull, active);       // inactive lanes count as done
+            if (kSoft) {
+                // same-row lanes of the batch: the first one collects the others' sums and adds them to the row's accumulator
+                // (a row's state belongs to this warp alone: no atomic)
+                const int leader = __ffs(peers) - 1;
+                unsigned rest = peers & ~(1u << leader);
+                while (__any_sync(kFull, rest != 0u)) {
+                    const int src = rest ? __ffs(rest) - 1 : lane;
+                    const float other = __shfl_sync(kFull, mass, src);
+                    if (rest && lane == leader) mass += other;
+                    rest &= rest - 1u;
+                }
+                if (active && lane == leader && mass != 0.f) l_s[rl] += mass;
+            }
+            // entries with candidates: same-row entries one after the other, in queue order
+            bool todo = active && min16(k) < INFINITY;
+            unsigned done_mask = ~__ballot_sync(kFull, todo);
             while (done_mask != kFull) {
                 const bool mine = todo && (__ffs(peers & ~done_mask) - 1 == lane);
                 // row state of the lanes whose turn it is
-                float xx = 0.f, thl = -INFINITY, thm = -INFINITY, kr = 0.f, r = 0.f, l = 0.f, worst = -INFINITY;
+                float xx = 0.f, thl = -INFINITY, thm = -INFINITY, kr = 0.f, c0 = 0.f, l_add = 0.f, worst = -INFINITY;
                 float2* L = lists + (mine ? rl : 0) * LIST_STRIDE;
                 if (mine) {
-                    xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; r = r_s[rl]; l = l_s[rl];
+                    xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; c0 = p.a2 * r_s[rl];
                     worst = worst_s[rl];
                     if (!kPrime && p.multi_split)
                         thl = fminf(thl, 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)))) - xx));
                 }
                 bool changed = false;
                 float prev = -INFINITY;                               // packed keys handled so far are <= prev
-                // warp-uniform loop: every trip handles the next-best key of every lane that still has one below its bound
+                // warp-uniform loop: every trip handles the next-best candidate key of every lane that still has one
                 for (;;) {
                     float m;
                     if (prev == -INFINITY) {                          // first trip of a lane: plain minimum
@@ -557,20 +601,12 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                         for (int t = 0; t < TC_CHUNK; ++t) cand[t] = k[t] > prev ? k[t] : INFINITY;
                         m = min16(cand);
                     }
-                    if (kSoft && mine && m < kr) {                    // new row minimum: move the reference of the mass
-                        const float rn = key_dist_approx(m, xx);
-                        if (l != 0.f) l *= ex2_approx(-p.a2 * (r - rn));
-                        kr = m; r = rn;
-                        const float te = rn + p.cut_over_alpha;
-                        thm = 0.5f * (te * te - xx);
-                    }
-                    const float lim = fminf(thl, worst);
-                    const bool go = mine && m < (kSoft ? fmaxf(lim, thm) : lim);
+                    const bool go = mine && m < INFINITY;             // every key below the snapshot is settled here: list or mass
                     if (!__any_sync(kFull, go)) break;
                     if (go) {
                         prev = m;
                         float out = m;
-                        if (m < lim) {                                // list candidate: replace the worst entry, find the new worst
+                        if (m < fminf(thl, worst)) {                  // still a candidate: replace the worst entry, find the new worst
                             out = worst;
                             const int ws = (int)(__float_as_uint(worst) & 15u);
                             L[ws] = make_float2(__uint_as_float((__float_as_uint(m) & ~15u) | (unsigned)ws),
@@ -580,13 +616,19 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                             for (int t = 0; t < K; ++t) w = fmaxf(w, L[t].x);
                             worst = w;
                             changed = true;
+                            if (kSoft && m < kr) {                    // new row minimum: the softmax window tightens (the reference stays r0)
+                                kr = m;
+                                const float te = key_dist_fast(m, xx) + p.cut_over_alpha;
+                                thm = fminf(thm, 0.5f * (te * te - xx));
+                            }
                         }
-                        if (kSoft && out < thm) l += ex2_approx(-p.a2 * (key_dist_approx(out, xx) - r));
+                        if (kSoft && out < LIST_EMPTY) l_add += ex2_approx(fmaf(-p.a2, key_dist_fast(out, xx), c0));
                     }
                 }
                 if (mine) {
                     thl = fminf(thl, worst);
-                    thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = l; worst_s[rl] = worst;
+                    thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; worst_s[rl] = worst;
+                    if (kSoft && l_add != 0.f) l_s[rl] += l_add;
                     *reinterpret_cast<volatile float*>(thr_hi_s + rl) = kSoft ? fmaxf(thl, thm) : thl;
                     if (!kPrime && p.multi_split && changed && worst < LIST_EMPTY)
                         atomicMin(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)), __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
@@ -619,7 +661,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                         if (m01 <= m23) { if (a0 <= a1) ++i0; else ++i1; } else { if (a2 <= a3) ++i2; else ++i3; }
                     }
                     const float m = fminf(fminf(L[0].x, L[KP].x), fminf(L2[0].x, L2[KP].x));
-                    if (w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
+                    if (p.prime_thr && w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
                     if (m < LIST_EMPTY) atomicMin(p.rmin_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, m, xx), 0.f)));
                 } else {
                     const size_t g_row = (size_t)b * p.N + row;
@@ -787,9 +829,14 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     }
     if (smem > 227 * 1024) { set_error("launch_cand_tc: C=%d needs %zu bytes of shared memory", C, smem); return DVM_ERR_UNSUPPORTED; }
     prof_begin(st);
-    if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 10th tile (10 % of the sweep's MMA work)
+    {
+        // priming pass over every 10th tile (10 % of the sweep's MMA work): list threshold + the FIXED softmax reference of every
+        // row.  Small problems (< 16 tiles) sample every other tile and only take the reference from it.
         TcParams pp = p;
-        pp.tile_stride = TC_PRIME_STRIDE; pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
+        const bool big = p.tiles_total >= TC_PRIME_MIN_TILES;
+        pp.tile_stride = big ? TC_PRIME_STRIDE : (p.tiles_total >= 2 ? 2 : 1);
+        pp.prime_thr = big ? 1 : 0;
+        pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
         dim3 gridp(2 * ceil_div(N, TC_BM), 1, B);                 // clusters of 2 CTAs along x
         kprime<<<gridp, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, pp);
         DVM_LAUNCH_CHECK();
