@@ -180,10 +180,11 @@ struct TcParams {
 // their two scanner warps with ONE LANE PER ENTRY (full lane utilisation whatever the rows are).  An entry's keys are split
 // against ONE snapshot of the row's list bound `lim`:
 //   * keys >= lim can never become candidates (bounds only tighten): their softmax terms exp2(c0 - a2 d) are summed by the
-//     lane at once.  The reference of the row's mass is FIXED (c0 = a2 * r0, r0 = the priming pass' sampled row minimum), so the
-//     terms of different entries of a row are independent: same-row lanes of a batch are pre-reduced with shuffles and the
-//     first of them adds the sum to the row's accumulator -- no serialisation, however many entries a row with a wide softmax
-//     window pushes (such rows used to serialise the whole batch: up to 16 passes of the list code per batch);
+//     lane at once, relative to the row's CURRENT reference distance r (read with the snapshot; it only moves in the
+//     serialised path below, which runs after these sums have been added): the terms of different entries of a row are
+//     independent, so same-row lanes of a batch are pre-reduced with shuffles and the first of them adds the sum to the
+//     row's accumulator -- no serialisation, however many entries a row with a wide softmax window pushes (such rows used
+//     to serialise the whole batch: up to 16 passes of the list code per batch);
 //   * keys < lim are list candidates: only these take the serialised path (same-row entries one after the other, in queue
 //     order): the key replaces the worst entry of the row's K-entry list in shared memory, what it evicts (or the key itself
 //     if the bound has tightened meanwhile) adds its term to the row's mass; the lane then publishes the row's new bound
@@ -310,8 +311,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
     float* thr_mass_s = thr_list_s + TC_BM;
     float* kr_s = thr_mass_s + TC_BM;                     // smallest key seen (tightens the softmax window)
-    float* r_s = kr_s + TC_BM;                            // r0: FIXED reference distance of the row's mass (priming pass)
-    float* l_s = r_s + TC_BM;                             // sum of exp2(-a2 (d - r0)) over the non-candidate columns
+    float* r_s = kr_s + TC_BM;                            // reference distance of the row's mass: starts at the priming pass' sampled minimum
+    float* l_s = r_s + TC_BM;                             // sum of exp2(-a2 (d - r)) over the non-candidate columns
     float* xx_s = l_s + TC_BM;                            // [256] |x~|^2
     float* worst_s = xx_s + TC_BM;                        // [256] largest key of the row's list (slot number in its low bits)
     QCtl* qctl = reinterpret_cast<QCtl*>(worst_s + TC_BM);   // [TC_CONS_WARPS]
@@ -354,9 +355,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             xx = __ldg(p.xx + (size_t)b * p.N + row);
             thl = kPrime ? INFINITY : 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row)) - xx);
             if (kSoft) {
-                // FIXED softmax reference from the priming pass (sample minimum >= row minimum: the window it gives is a
-                // superset).  A row without a finite sample keeps r = +inf: its terms become NaN and finalize sends it to
-                // the exact path.
+                // softmax reference from the priming pass (sample minimum >= row minimum: the window it gives is a superset)
                 const float d2s = __uint_as_float(__ldcg(p.rmin_global + (size_t)b * p.N + row));
                 thm = INFINITY;
                 if (d2s < INFINITY) {
@@ -580,10 +579,10 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             while (done_mask != kFull) {
                 const bool mine = todo && (__ffs(peers & ~done_mask) - 1 == lane);
                 // row state of the lanes whose turn it is
-                float xx = 0.f, thl = -INFINITY, thm = -INFINITY, kr = 0.f, c0 = 0.f, l_add = 0.f, worst = -INFINITY;
+                float xx = 0.f, thl = -INFINITY, thm = -INFINITY, kr = 0.f, r = 0.f, l = 0.f, worst = -INFINITY;
                 float2* L = lists + (mine ? rl : 0) * LIST_STRIDE;
                 if (mine) {
-                    xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; c0 = p.a2 * r_s[rl];
+                    xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; r = r_s[rl]; l = l_s[rl];
                     worst = worst_s[rl];
                     if (!kPrime && p.multi_split)
                         thl = fminf(thl, 0.5f * (__uint_as_float(__ldcg(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)))) - xx));
@@ -605,6 +604,13 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     if (!__any_sync(kFull, go)) break;
                     if (go) {
                         prev = m;
+                        if (kSoft && m < kr) {                        // new row minimum: move the reference of the row's mass
+                            const float rn = key_dist_fast(m, xx);
+                            if (l != 0.f) l *= ex2_approx(-p.a2 * (r - rn));
+                            kr = m; r = rn;
+                            const float te = rn + p.cut_over_alpha;
+                            thm = 0.5f * (te * te - xx);
+                        }
                         float out = m;
                         if (m < fminf(thl, worst)) {                  // still a candidate: replace the worst entry, find the new worst
                             out = worst;
@@ -616,19 +622,13 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                             for (int t = 0; t < K; ++t) w = fmaxf(w, L[t].x);
                             worst = w;
                             changed = true;
-                            if (kSoft && m < kr) {                    // new row minimum: the softmax window tightens (the reference stays r0)
-                                kr = m;
-                                const float te = key_dist_fast(m, xx) + p.cut_over_alpha;
-                                thm = fminf(thm, 0.5f * (te * te - xx));
-                            }
                         }
-                        if (kSoft && out < LIST_EMPTY) l_add += ex2_approx(fmaf(-p.a2, key_dist_fast(out, xx), c0));
+                        if (kSoft && out < LIST_EMPTY) l += ex2_approx(-p.a2 * (key_dist_fast(out, xx) - r));
                     }
                 }
                 if (mine) {
                     thl = fminf(thl, worst);
-                    thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; worst_s[rl] = worst;
-                    if (kSoft && l_add != 0.f) l_s[rl] += l_add;
+                    thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = l; worst_s[rl] = worst;
                     *reinterpret_cast<volatile float*>(thr_hi_s + rl) = kSoft ? fmaxf(thl, thm) : thl;
                     if (!kPrime && p.multi_split && changed && worst < LIST_EMPTY)
                         atomicMin(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)), __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
