@@ -301,6 +301,7 @@ struct FinalizeArgs {
     int* flag_list; int* flag_count;               // rows failing the certificate (may be null)
     float* flag_thr; float* flag_r;                // per flag slot: squared scan threshold, reference distance (may be null)
     int* tie_count;                                // counts uncertified rows when flag_list is null
+    int* nonfinite_count;                          // rows whose 16-bit softmax mass came out non-finite (settled exactly)
     int64_t* argmin; int* top_idx; float* top_w; float* top_d; float* row_min; float* row_sum; float* PiV;
 };
 
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
         }
         // the 16-bit pass sums its softmax mass against a FIXED per-row reference (the priming pass' sampled minimum): a row
         // without a finite sample, or one whose terms overflowed against it, has a non-finite mass and is settled exactly
-        if (kSoft && !(l_tot < INFINITY)) ok = false;
+        if (kSoft && !(l_tot < INFINITY)) { ok = false; if (a.nonfinite_count) atomicAdd(a.nonfinite_count, 1); }
         if (!ok) {
             if (a.flag_list) {
                 const int e = atomicAdd(a.flag_count, 1);
@@ -797,7 +798,7 @@ static int softmap_fwd_impl(const float* X, const float* Y, const float* V,
     }
     if ((rc = launch_cand_tc(X, Y, B, N, M, C, alpha, soft, prec, tc, err_x, err_ymax, &fa.tc_xx, &fa.tc_yymax, tws, tws_bytes, st))) return rc;
     fa.cb = tc; fa.rel_bound = 2e-5f; fa.err_x = err_x; fa.err_ymax = err_ymax;
-    fa.flag_list = flag_list; fa.flag_count = st_out; fa.flag_thr = rw.flag_thr; fa.flag_r = rw.flag_r;
+    fa.flag_list = flag_list; fa.flag_count = st_out; fa.flag_thr = rw.flag_thr; fa.flag_r = rw.flag_r; fa.nonfinite_count = st_out + 3;
     DVM_CUDA(cudaMemsetAsync(rw.cnt, 0, RESC_MAX * sizeof(int), st));
     if ((rc = launch_finalize(fa, soft, rows, st))) return rc;
     // rows the certificate rejected (count lives on the device: no host sync, every kernel below exits at once
@@ -821,7 +822,7 @@ static int softmap_fwd_impl(const float* X, const float* Y, const float* V,
         }
         RescueArgs ra{flag_list, st_out, rw.flag_r, rw.cnt, rw.idx, rw.mass, nch, rw.list2, st_out + 2, nch <= RESC_NCH_MAX ? 1 : 0};
         FinalizeArgs fr = fa;
-        fr.flag_list = nullptr; fr.flag_count = nullptr; fr.flag_thr = nullptr; fr.flag_r = nullptr; fr.tie_count = nullptr;
+        fr.flag_list = nullptr; fr.flag_count = nullptr; fr.flag_thr = nullptr; fr.flag_r = nullptr; fr.tie_count = nullptr; fr.nonfinite_count = nullptr;
         const int fgrid = ceil_div(RESC_MAX, FIN_WARPS);
         if (soft) rescue_finalize_kernel<true><<<fgrid, FIN_WARPS * 32, 0, st>>>(fr, ra);
         else      rescue_finalize_kernel<false><<<fgrid, FIN_WARPS * 32, 0, st>>>(fr, ra);
@@ -832,7 +833,7 @@ static int softmap_fwd_impl(const float* X, const float* Y, const float* V,
     if ((rc = launch_cand_simt(X, Y, B, N, M, C, alpha, soft, list2, count2, rows, simt, st))) return rc;
     fa.cb = simt; fa.rel_bound = 1e-5f; fa.err_x = nullptr; fa.err_ymax = nullptr; fa.tc_xx = nullptr; fa.tc_yymax = nullptr;
     fa.row_list = list2; fa.row_count = count2; fa.flag_list = nullptr; fa.flag_count = nullptr; fa.flag_thr = nullptr; fa.flag_r = nullptr;
-    fa.tie_count = st_out + 1;
+    fa.tie_count = st_out + 1; fa.nonfinite_count = nullptr;
     return launch_finalize(fa, soft, rows, st);
 }
 

@@ -156,6 +156,8 @@ struct TcParams {
     int tiles_total, tiles_per_split;
     int tile_stride;             // 1 for the sweep; > 1: the priming pass visits every tile_stride-th tile only
     int multi_split;             // column-split CTAs exchange thresholds through thr_global during the sweep
+    int debug;                   // DVM_TC_DEBUG experiment switches (0 in production): 1 = scanners never push, 2 = scanners only drain
+                                 // TMEM (no min-tree), 4 = accumulator wait without nanosleep back-off, 8 = consumers discard entries
     int prime_thr;               // priming pass: also publish the list threshold (0 for small problems: the sample is too small
                                  // for its 8th smallest chunk minimum to leave 16 candidates below it -- only the softmax reference)
     float a2, cut_over_alpha;
@@ -240,48 +242,64 @@ __device__ __forceinline__ float max16(const float (&k)[16]) {
                  max3(max3(k[9], k[10], k[11]), max3(k[12], k[13], k[14]), k[15]));
 }
 
-// scanner: one 16-column chunk of one row.
-// kPrivBound (hard mode): while the consumer has not published a list threshold yet (first tile of a CTA that starts
-// without a primed threshold) the thread bounds it itself -- the largest key of any chunk it has seen is >= the row's
-// 16th smallest key -- so the start-up does not flood the queue with every chunk of every row.
 // makes the ring entries written so far by all lanes of the warp visible to the consumer: tail word at `tail_a`
 __device__ __forceinline__ void ring_publish(uint32_t tail_a, unsigned tail, int lane) {
     __syncwarp();                                                    // orders the lanes' entry stores before lane 0's release
     if (lane == 0) sts_u32_release(tail_a, tail);
 }
 
-template <bool kPrivBound>
-__device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase, uint32_t thr_hi_a, uint32_t q_a, uint32_t head_a,
-                                           int row_in_q, int lane, float& priv, bool first_tile, unsigned& tail, unsigned& head_seen,
-                                           unsigned& pub) {
-    float th = lds_f32(thr_hi_a);
-    if (kPrivBound) {
-        th = fminf(th, priv);
-        if (first_tile) priv = fminf(priv, max16(k));
+// A scanner warp's single-producer ring: everything lives in (warp-uniform) registers; the consumer's head is re-read only when
+// the ring looks full.  Entries are PUBLISHED (one fence + the tail word) once per tile.
+struct ScanRing {
+    uint32_t base;           // shared-window address of slot 0
+    uint32_t head_a;         // ... of the consumer's head word; the published tail sits at head_a + 8
+    unsigned tail, head_seen, pub;
+};
+
+// rare: kept out of the scan loop, and by VALUE (a reference would pin the ring state to local memory)
+__device__ __noinline__ uint2 ring_wait_space(uint32_t head_a, unsigned tail, unsigned pub, int n, int lane) {
+    unsigned head_seen;
+    for (;;) {
+        if (pub != tail) { ring_publish(head_a + 8, tail, lane); pub = tail; }   // the consumer must see what it has to free
+        head_seen = lds_u32_volatile(head_a);
+        if ((int)(tail + (unsigned)n - head_seen) <= Q_SUB) break;
+        __nanosleep(20);
     }
-    const bool slow = min16(k) < th;
+    return make_uint2(head_seen, pub);
+}
+
+// the lanes whose chunk can matter (`slow`) copy the WHOLE chunk (16 keys, row, first column) into the warp's ring
+__device__ __forceinline__ void push_chunk(const float (&k)[TC_CHUNK], int cbase, bool slow, ScanRing& rg, int lane, unsigned lanes_below) {
     const unsigned mask = __ballot_sync(kFull, slow);
     if (mask == 0u) return;                                          // warp-uniform
-    // the ring has ONE producer (this warp): the tail is a warp-uniform register, no atomic; the consumer's head is
-    // re-read only when the ring looks full.  Entries are PUBLISHED (one fence + the tail word) once per tile, at a
-    // point where the warp has nothing in flight -- a release per entry drained the TMEM-load pipeline every time.
     const int n = __popc(mask);
-    while ((int)(tail + (unsigned)n - head_seen) > Q_SUB) {
-        if (pub != tail) { ring_publish(head_a + 8, tail, lane); pub = tail; }     // the consumer must see what it has to free
-        head_seen = lds_u32_volatile(head_a);
-        if ((int)(tail + (unsigned)n - head_seen) > Q_SUB) __nanosleep(20);
+    if ((int)(rg.tail + (unsigned)n - rg.head_seen) > Q_SUB) {
+        const uint2 hp = ring_wait_space(rg.head_a, rg.tail, rg.pub, n, lane);
+        rg.head_seen = hp.x; rg.pub = hp.y;
     }
     if (slow) {
-        const unsigned g = tail + (unsigned)__popc(mask & ((1u << lane) - 1u));
-        const uint32_t ea = q_a + (g % Q_SUB) * Q_ENTRY;
+        const unsigned g = rg.tail + (unsigned)__popc(mask & lanes_below);
+        const uint32_t ea = rg.base + (g & (unsigned)(Q_SUB - 1)) * Q_ENTRY;
         sts_v4(ea, k[0], k[1], k[2], k[3]);
         sts_v4(ea + 16, k[4], k[5], k[6], k[7]);
         sts_v4(ea + 32, k[8], k[9], k[10], k[11]);
         sts_v4(ea + 48, k[12], k[13], k[14], k[15]);
-        sts_v2(ea + 64, __int_as_float(row_in_q), __int_as_float(cbase));
+        sts_v2(ea + 64, __int_as_float(lane), __int_as_float(cbase));
     }
-    tail += (unsigned)n;
-    if (n >= 8) { ring_publish(head_a + 8, tail, lane); pub = tail; }   // flood (start-up, dense softmax windows): do not sit on the entries
+    rg.tail += (unsigned)n;
+    if (n >= 8) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }   // flood (start-up, dense softmax windows): do not sit on the entries
+}
+
+// one tile of one scanner thread: its row x 64 columns.  Four min-trees (8 three-input min instructions each), ONE vote for
+// the common "nothing below the bound" case, then a vote + push per chunk.
+__device__ __forceinline__ void scan_tile(const float (&k0)[TC_CHUNK], const float (&k1)[TC_CHUNK], const float (&k2)[TC_CHUNK],
+                                          const float (&k3)[TC_CHUNK], int col0, float th, ScanRing& rg, int lane, unsigned lanes_below) {
+    const bool s0 = min16(k0) < th, s1 = min16(k1) < th, s2 = min16(k2) < th, s3 = min16(k3) < th;
+    if (!__any_sync(kFull, s0 || s1 || s2 || s3)) return;
+    push_chunk(k0, col0, s0, rg, lane, lanes_below);
+    push_chunk(k1, col0 + TC_CHUNK, s1, rg, lane, lanes_below);
+    push_chunk(k2, col0 + 2 * TC_CHUNK, s2, rg, lane, lanes_below);
+    push_chunk(k3, col0 + 3 * TC_CHUNK, s3, rg, lane, lanes_below);
 }
 
 // priming pass: the scanner thread keeps the KP smallest CHUNK MINIMA it has seen in a sorted register list (a branch-free
@@ -367,7 +385,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
         thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = 0.f; xx_s[rl] = xx;
         worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
-        thr_hi_s[rl] = kSoft ? fmaxf(thl, thm) : thl;
+        thr_hi_s[rl] = (p.debug & 1) ? -INFINITY : (kSoft ? fmaxf(thl, thm) : thl);
     }
     if (warp == 1) {                        // TMEM of the pair: 512 columns per CTA (2 accumulator stages x 256), same warp in both CTAs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
@@ -451,29 +469,31 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int ch = cgp >> 1;                           // column half: the list / consumer this warp feeds
         const int cq = ch * 4 + quarter;                   // consumer / queue of this warp's (rows, column half)
         const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 4u;
-        const uint32_t q_a = smem_u32(q_mem) + (uint32_t)(cq * Q_CAP + (cgp & 1) * Q_SUB) * Q_ENTRY;   // this warp's own ring
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
-        const uint32_t head_a = ctl_a + (uint32_t)(cgp & 1) * 4u;
-        unsigned q_tail = 0, q_head_seen = 0, q_pub = 0;
+        ScanRing rg;
+        rg.base = smem_u32(q_mem) + (uint32_t)(cq * Q_CAP + (cgp & 1) * Q_SUB) * Q_ENTRY;   // this warp's own ring
+        rg.head_a = ctl_a + (uint32_t)(cgp & 1) * 4u;
+        rg.tail = rg.head_seen = rg.pub = 0u;
+        const unsigned lanes_below = (1u << lane) - 1u;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgp * 64;
-        float priv = INFINITY;
         float pl[KP];
 #pragma unroll
         for (int t = 0; t < KP; ++t) pl[t] = INFINITY;
-#pragma unroll 1
-        for (int it = 0; it < ntiles; ++it) {
-            const int acc = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
-            const int col0 = (tile0 + it * p.tile_stride) * TC_BN + cgp * 64;
-            mbar_wait_backoff(tfull + acc, aph);
+        int col0 = tile0 * TC_BN + cgp * 64;
+        const int col_step = p.tile_stride * TC_BN;
+        uint32_t aph = 0;
+        // one tile: wait for the accumulator stage, pull this thread's 64 columns into registers (four TMEM loads in flight,
+        // one wait), hand the stage back at once, then scan
+        auto tile = [&](const int acc) {
+            if (p.debug & 4) mbar_wait(tfull + acc, aph); else mbar_wait_backoff(tfull + acc, aph);
             tc_fence_after();
             const uint32_t taddr = t_lane + acc * TC_BN;
-            // the whole 64-column slice of this thread's row: four TMEM loads in flight, one wait, stage handed back at once
             float k0[TC_CHUNK], k1[TC_CHUNK], k2[TC_CHUNK], k3[TC_CHUNK];
             tc_ld16_issue(taddr, k0);
             tc_ld16_issue(taddr + TC_CHUNK, k1);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, k2);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, k3);
+            const float th = kPrime ? 0.f : lds_f32(thr_hi_a);      // the row's published bound: one read per tile
             tc_ld16_wait(k0);
             tc_ld16_after_wait(k1); tc_ld16_after_wait(k2); tc_ld16_after_wait(k3);
             tc_fence_before();
@@ -481,14 +501,17 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             if (lane == 0) mbar_arrive_leader(tempty + acc);
             if (kPrime) {
                 prime_chunk(k0, pl); prime_chunk(k1, pl); prime_chunk(k2, pl); prime_chunk(k3, pl);
+            } else if (p.debug & 2) {
+                if (k0[0] + k1[1] + k2[2] + k3[3] == 12345.678f) pl[0] = 0.f;      // keep the loads alive
             } else {
-                scan_chunk<!kSoft>(k0, col0, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-                scan_chunk<!kSoft>(k1, col0 + TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-                scan_chunk<!kSoft>(k2, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-                scan_chunk<!kSoft>(k3, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub);
-                if (q_pub != q_tail) { ring_publish(head_a + 8, q_tail, lane); q_pub = q_tail; }     // once per tile
+                scan_tile(k0, k1, k2, k3, col0, th, rg, lane, lanes_below);
+                if (rg.pub != rg.tail) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }     // once per tile
             }
-        }
+            col0 += col_step;
+        };
+#pragma unroll 1
+        for (int it = 0; it + 1 < ntiles; it += 2) { tile(0); tile(1); aph ^= 1u; }
+        if (ntiles & 1) tile(0);
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
             float2* L = lists + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
 #pragma unroll
@@ -531,11 +554,12 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 __nanosleep(32);
                 continue;
             }
-            const bool active = (lane & 15) < (sub ? n1 : n0);
+            const bool active = (lane & 15) < (sub ? n1 : n0) && !(p.debug & 8);
             float k[TC_CHUNK];
             int rl = -1 - lane, cbase = 0;                            // inactive lanes: unique pseudo rows
             float lim = -INFINITY;                                    // ONE snapshot of the row's list bound per entry
-            float mass = 0.f;
+            float mass = 0.f, thm_e = -INFINITY;
+            bool need_mass = false;
             if (active) {
                 const float4 k0 = lds_v4(ea), k1 = lds_v4(ea + 16), k2 = lds_v4(ea + 32), k3 = lds_v4(ea + 48);
                 k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
@@ -544,21 +568,32 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 rl = rl0 + __float_as_int(rc.x); cbase = __float_as_int(rc.y);
                 lim = fminf(thr_list_s[rl], worst_s[rl]);
                 if (kSoft) {
-                    // terms of the keys that can never be candidates (>= lim), inside the softmax window: fixed reference r0
-                    const float xx = xx_s[rl], thm = thr_mass_s[rl], c0 = p.a2 * r_s[rl];
+                    // does the entry hold a NON-candidate key (>= lim) inside the softmax window?  (one min-tree; most entries
+                    // of a peaked softmax only carry their candidate)
+                    thm_e = thr_mass_s[rl];
+                    float nc[TC_CHUNK];
 #pragma unroll
-                    for (int t = 0; t < TC_CHUNK; ++t) {
-                        const float e = ex2_approx(fmaf(-p.a2, key_dist_fast(k[t], xx), c0));
-                        if (k[t] >= lim && k[t] < thm) mass += e;
-                    }
+                    for (int t = 0; t < TC_CHUNK; ++t) nc[t] = k[t] >= lim ? k[t] : INFINITY;
+                    need_mass = min16(nc) < thm_e;
                 }
-#pragma unroll
-                for (int t = 0; t < TC_CHUNK; ++t)                    // candidates keep their column offset in the 4 low bits
-                    k[t] = k[t] < lim ? __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t) : INFINITY;
             } else {
 #pragma unroll
                 for (int t = 0; t < TC_CHUNK; ++t) k[t] = INFINITY;
             }
+            if (kSoft && __any_sync(kFull, need_mass)) {
+                // terms of the keys that can never be candidates (>= lim), inside the softmax window, against the snapshot reference
+                if (need_mass) {
+                    const float xx = xx_s[rl], c0 = p.a2 * r_s[rl];
+#pragma unroll
+                    for (int t = 0; t < TC_CHUNK; ++t) {
+                        const float e = ex2_approx(fmaf(-p.a2, key_dist_fast(k[t], xx), c0));
+                        if (k[t] >= lim && k[t] < thm_e) mass += e;
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < TC_CHUNK; ++t)                        // candidates keep their column offset in the 4 low bits
+                k[t] = k[t] < lim ? __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t) : INFINITY;
             const unsigned peers = __match_any_sync(kFull, rl);
             if (kSoft) {
                 // same-row lanes of the batch: the first one collects the others' sums and adds them to the row's accumulator
@@ -623,7 +658,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                             worst = w;
                             changed = true;
                         }
-                        if (kSoft && out < LIST_EMPTY) l += ex2_approx(-p.a2 * (key_dist_fast(out, xx) - r));
+                        // evicted / rejected key inside the softmax window (empty-slot markers are ~3e38: never)
+                        if (kSoft && out < fminf(thm, 1e37f)) l += ex2_approx(-p.a2 * (key_dist_fast(out, xx) - r));
                     }
                 }
                 if (mine) {
@@ -810,6 +846,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     p.xx = w.xx; p.cb = cb;
     p.thr_global = w.thr_g;
     p.rmin_global = w.rmin_g;
+    { const char* e = getenv("DVM_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     p.multi_split = 1;                               // the two column halves of a tile are separate lists that share thresholds
     p.tile_stride = 1;
     fill_u32_kernel<<<ceil_div(2 * B * N, 256), 256, 0, st>>>(w.thr_g, 0x7f800000u, 2 * B * N);    // +inf (memset cannot write it)

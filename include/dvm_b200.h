@@ -70,7 +70,7 @@ int         dvm_profile_read_channel(int channel, double* total_ms, int* bracket
  *   PiV     f32[B,N,Dv]
  *   stats   int32[4]: [0] rows whose top-k the 16-bit candidate pass could not certify (settled exactly by the
  *                     rescue scan), [1] exact fp32 near-ties at rank topk / topk+1, [2] rows that needed the full
- *                     fp32 candidate pass, [3] reserved
+ *                     fp32 candidate pass, [3] rows whose 16-bit softmax mass was non-finite (counted in [0])
  * ------------------------------------------------------------------------------------------ */
 size_t dvm_softmap_workspace_bytes(int B, int N, int M, int C, int prec);
 int dvm_softmap_fwd(const float* X, const float* Y, const float* V,
