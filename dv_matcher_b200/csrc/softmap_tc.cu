@@ -203,7 +203,7 @@ constexpr int KP = 8;                  // list length of the priming pass
 constexpr int Q_CAP = 64;              // queue slots per consumer: two single-producer rings of Q_SUB slots
 constexpr int Q_SUB = Q_CAP / 2;       // one ring per scanner warp feeding the consumer
 constexpr int Q_ENTRY = 80;            // bytes: 16 keys | row, first column | sequence word, pad
-constexpr int LIST_STRIDE = KC + 1;    // float2 per row (odd stride in 8-byte units: conflict-poor)
+constexpr int LIST_STRIDE = KC;        // a list = 16 keys (64 B, read back as four 16-byte loads) + 16 column indices, in two arrays
 constexpr float LIST_EMPTY = 3.0e38f;  // "no entry" key (finite, so that a slot number can live in its low mantissa bits)
 
 struct QCtl { unsigned head0, head1, tail0, tail1, done, pad0, pad1, pad2; };   // ring heads (consumer writes), published tails
@@ -324,8 +324,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     uint8_t* Ys = Xs + unit;                              // [NST][KB x 16 KB | 4 KB]: this CTA's 128 columns of every tile (half of N)
     uint8_t* q_mem = Ys + TC_NST * unit;                  // [TC_CONS_WARPS][Q_CAP][Q_ENTRY]
     // lists and row state are indexed by  li = column half * 128 + CTA-local row  (a row has one list per column half of the tile)
-    float2* lists = reinterpret_cast<float2*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][LIST_STRIDE] (key, idx)
-    float* thr_hi_s = reinterpret_cast<float*>(lists + TC_BM * LIST_STRIDE);           // [256] bound read by the scanners
+    float* lkeys = reinterpret_cast<float*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][16] list keys (16-byte aligned rows)
+    int* lidx = reinterpret_cast<int*>(lkeys + TC_BM * LIST_STRIDE);                    // [256][16] list column indices
+    float* thr_hi_s = reinterpret_cast<float*>(lidx + TC_BM * LIST_STRIDE);             // [256] bound read by the scanners
     float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
     float* thr_mass_s = thr_list_s + TC_BM;
     float* kr_s = thr_mass_s + TC_BM;                     // smallest key seen (tightens the softmax window)
@@ -364,8 +365,10 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
     // row state, lists and queue sequence words (all threads)
     for (int e = threadIdx.x; e < TC_CONS_WARPS * Q_CAP; e += TC_THREADS) *reinterpret_cast<unsigned*>(q_mem + e * Q_ENTRY + 72) = 0u;
-    for (int e = threadIdx.x; e < TC_BM * LIST_STRIDE; e += TC_THREADS)      // empty slots: LIST_EMPTY with the slot number in the low bits
-        lists[e] = make_float2(__uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)((e % LIST_STRIDE) & 15)), __int_as_float(-1));
+    for (int e = threadIdx.x; e < TC_BM * LIST_STRIDE; e += TC_THREADS) {    // empty slots: LIST_EMPTY with the slot number in the low bits
+        lkeys[e] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(e & 15));
+        lidx[e] = -1;
+    }
     for (int rl = threadIdx.x; rl < TC_BM; rl += TC_THREADS) {        // rl = li: both column halves start from the same state
         const int row = row0 + (rl & (TC_SUB - 1));
         float thl = -INFINITY, thm = -INFINITY, kr = INFINITY, r = INFINITY, xx = 0.f;   // padding rows never enqueue
@@ -513,9 +516,9 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         for (int it = 0; it + 1 < ntiles; it += 2) { tile(0); tile(1); aph ^= 1u; }
         if (ntiles & 1) tile(0);
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
-            float2* L = lists + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
+            float* L = lkeys + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
 #pragma unroll
-            for (int t = 0; t < KP; ++t) L[t] = make_float2(pl[t], 0.f);
+            for (int t = 0; t < KP; ++t) L[t] = pl[t];
         }
         __syncwarp();
         if (lane == 0) {
@@ -594,6 +597,15 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll
             for (int t = 0; t < TC_CHUNK; ++t)                        // candidates keep their column offset in the 4 low bits
                 k[t] = k[t] < lim ? __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t) : INFINITY;
+            // the two smallest candidates of every entry, once per batch
+            const float m1 = min16(k);
+            float m2;
+            {
+                float cand[TC_CHUNK];
+#pragma unroll
+                for (int t = 0; t < TC_CHUNK; ++t) cand[t] = k[t] > m1 ? k[t] : INFINITY;
+                m2 = min16(cand);
+            }
             const unsigned peers = __match_any_sync(kFull, rl);
             if (kSoft) {
                 // same-row lanes of the batch: the first one collects the others' sums and adds them to the row's accumulator
@@ -609,13 +621,13 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 if (active && lane == leader && mass != 0.f) l_s[rl] += mass;
             }
             // entries with candidates: same-row entries one after the other, in queue order
-            bool todo = active && min16(k) < INFINITY;
+            bool todo = active && m1 < INFINITY;
             unsigned done_mask = ~__ballot_sync(kFull, todo);
             while (done_mask != kFull) {
                 const bool mine = todo && (__ffs(peers & ~done_mask) - 1 == lane);
                 // row state of the lanes whose turn it is
                 float xx = 0.f, thl = -INFINITY, thm = -INFINITY, kr = 0.f, r = 0.f, l = 0.f, worst = -INFINITY;
-                float2* L = lists + (mine ? rl : 0) * LIST_STRIDE;
+                const int lb = (mine ? rl : 0) * LIST_STRIDE;
                 if (mine) {
                     xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; r = r_s[rl]; l = l_s[rl];
                     worst = worst_s[rl];
@@ -624,12 +636,13 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 }
                 bool changed = false;
                 float prev = -INFINITY;                               // packed keys handled so far are <= prev
-                // warp-uniform loop: every trip handles the next-best candidate key of every lane that still has one
-                for (;;) {
+                // warp-uniform loop: every trip handles the next-best candidate key of every lane that still has one.  The two
+                // smallest were found once per batch (m1, m2): the common single-candidate entry costs no second min-tree.
+                for (int trip = 0;; ++trip) {
                     float m;
-                    if (prev == -INFINITY) {                          // first trip of a lane: plain minimum
-                        m = min16(k);
-                    } else {
+                    if (trip == 0) m = m1;
+                    else if (trip == 1) m = m2;
+                    else {
                         float cand[TC_CHUNK];
 #pragma unroll
                         for (int t = 0; t < TC_CHUNK; ++t) cand[t] = k[t] > prev ? k[t] : INFINITY;
@@ -650,11 +663,15 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                         if (m < fminf(thl, worst)) {                  // still a candidate: replace the worst entry, find the new worst
                             out = worst;
                             const int ws = (int)(__float_as_uint(worst) & 15u);
-                            L[ws] = make_float2(__uint_as_float((__float_as_uint(m) & ~15u) | (unsigned)ws),
-                                                __int_as_float(cbase + (int)(__float_as_uint(m) & 15u)));
-                            float w = -INFINITY;
-#pragma unroll
-                            for (int t = 0; t < K; ++t) w = fmaxf(w, L[t].x);
+                            lkeys[lb + ws] = __uint_as_float((__float_as_uint(m) & ~15u) | (unsigned)ws);
+                            lidx[lb + ws] = cbase + (int)(__float_as_uint(m) & 15u);
+                            const float4* L4 = reinterpret_cast<const float4*>(lkeys + lb);
+                            const float4 a0 = L4[0], a1 = L4[1];
+                            float w = max3(max3(a0.x, a0.y, a0.z), max3(a0.w, a1.x, a1.y), fmaxf(a1.z, a1.w));
+                            if (K > 8) {
+                                const float4 a2 = L4[2], a3 = L4[3];
+                                w = max3(w, max3(max3(a2.x, a2.y, a2.z), max3(a2.w, a3.x, a3.y), fmaxf(a3.z, a3.w)), w);
+                            }
                             worst = w;
                             changed = true;
                         }
@@ -682,21 +699,21 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const int row = row0 + (rl & (TC_SUB - 1));
             if (row < p.N && (!kPrime || cw < 4)) {
                 const float xx = xx_s[rl];
-                const float2* L = lists + rl * LIST_STRIDE;
+                const float* L = lkeys + rl * LIST_STRIDE;
                 if (kPrime) {
                     // merge the four sorted lists of chunk minima (column groups; two sit in the other half's list slot):
                     // KP-th smallest of the union, and the minimum
-                    const float2* L2 = L + TC_SUB * LIST_STRIDE;
+                    const float* L2 = L + TC_SUB * LIST_STRIDE;
                     int i0 = 0, i1 = KP, i2 = 0, i3 = KP;
                     float w = INFINITY;
                     for (int t = 0; t < KP; ++t) {
-                        const float a0 = i0 < KP ? L[i0].x : INFINITY, a1 = i1 < 2 * KP ? L[i1].x : INFINITY;
-                        const float a2 = i2 < KP ? L2[i2].x : INFINITY, a3 = i3 < 2 * KP ? L2[i3].x : INFINITY;
+                        const float a0 = i0 < KP ? L[i0] : INFINITY, a1 = i1 < 2 * KP ? L[i1] : INFINITY;
+                        const float a2 = i2 < KP ? L2[i2] : INFINITY, a3 = i3 < 2 * KP ? L2[i3] : INFINITY;
                         const float m01 = fminf(a0, a1), m23 = fminf(a2, a3);
                         w = fminf(m01, m23);
                         if (m01 <= m23) { if (a0 <= a1) ++i0; else ++i1; } else { if (a2 <= a3) ++i2; else ++i3; }
                     }
-                    const float m = fminf(fminf(L[0].x, L[KP].x), fminf(L2[0].x, L2[KP].x));
+                    const float m = fminf(fminf(L[0], L[KP]), fminf(L2[0], L2[KP]));
                     if (p.prime_thr && w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
                     if (m < LIST_EMPTY) atomicMin(p.rmin_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, m, xx), 0.f)));
                 } else {
@@ -704,10 +721,10 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const int part = split * 2 + (cw >> 2);                 // partial list index: (column split, column half)
                     const size_t base = (g_row * p.cb.P + part) * KC;
                     for (int t = 0; t < K; ++t) {
-                        const float2 e = L[t];
-                        const bool has = e.x < LIST_EMPTY;
-                        p.cb.key[base + t] = has ? fmaxf(fmaf(2.f, e.x, xx), 0.f) : INFINITY;      // back to the true d^2 domain
-                        p.cb.idx[base + t] = has ? __float_as_int(e.y) : -1;
+                        const float ek = L[t];
+                        const bool has = ek < LIST_EMPTY;
+                        p.cb.key[base + t] = has ? fmaxf(fmaf(2.f, ek, xx), 0.f) : INFINITY;       // back to the true d^2 domain
+                        p.cb.idx[base + t] = has ? lidx[rl * LIST_STRIDE + t] : -1;
                     }
                     const float thl = thr_list_s[rl];
                     p.cb.l[g_row * p.cb.P + part] = l_s[rl];
