@@ -290,12 +290,44 @@ __device__ __forceinline__ void push_chunk(const float (&k)[TC_CHUNK], int cbase
     if (n >= 8) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }   // flood (start-up, dense softmax windows): do not sit on the entries
 }
 
+// softmax terms of one chunk against the fixed per-row reference (c0 = a2 * r0): exp2(c0 - a2 d), d = sqrt(2 key + |x~|^2)
+__device__ __forceinline__ float chunk_mass(const float (&k)[TC_CHUNK], float xx, float c0, float a2) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < TC_CHUNK; t += 2) {
+        s0 += ex2_approx(fmaf(-a2, key_dist_fast(k[t], xx), c0));
+        s1 += ex2_approx(fmaf(-a2, key_dist_fast(k[t + 1], xx), c0));
+    }
+    return s0 + s1;
+}
+
+constexpr int TC_DENSE_LANES = 8;      // lanes of a warp with in-window non-candidate chunks from which the warp sums them itself
+
 // one tile of one scanner thread: its row x 64 columns.  Four min-trees (8 three-input min instructions each), ONE vote for
-// the common "nothing below the bound" case, then a vote + push per chunk.
+// the common "nothing below the bounds" case, then a vote + push per chunk.  thr = (list bound, softmax-window bound) of the row.
+// Dense-window mode (kSoft): when many lanes of the warp hold chunks that lie inside their row's softmax window but cannot be
+// list candidates (small alpha: every chunk of every row), pushing them through the queues would make the consumers the
+// bottleneck (22-140 TFLOP/s at alpha = 10); the lanes then add the 16 terms of such a chunk to a private accumulator
+// (fixed reference r0 of the priming pass, merged with the consumers' mass at the end) and only candidate chunks are pushed.
+template <bool kSoft>
 __device__ __forceinline__ void scan_tile(const float (&k0)[TC_CHUNK], const float (&k1)[TC_CHUNK], const float (&k2)[TC_CHUNK],
-                                          const float (&k3)[TC_CHUNK], int col0, float th, ScanRing& rg, int lane, unsigned lanes_below) {
-    const bool s0 = min16(k0) < th, s1 = min16(k1) < th, s2 = min16(k2) < th, s3 = min16(k3) < th;
+                                          const float (&k3)[TC_CHUNK], int col0, float2 thr, ScanRing& rg, int lane, unsigned lanes_below,
+                                          float xx, float c0, float a2, float& l_scan) {
+    const float c_0 = min16(k0), c_1 = min16(k1), c_2 = min16(k2), c_3 = min16(k3);
+    const float th = kSoft ? fmaxf(thr.x, thr.y) : thr.x;
+    bool s0 = c_0 < th, s1 = c_1 < th, s2 = c_2 < th, s3 = c_3 < th;
     if (!__any_sync(kFull, s0 || s1 || s2 || s3)) return;
+    if (kSoft) {
+        // in-window chunks that hold no list candidate
+        const bool w0 = s0 && c_0 >= thr.x, w1 = s1 && c_1 >= thr.x, w2 = s2 && c_2 >= thr.x, w3 = s3 && c_3 >= thr.x;
+        if (__popc(__ballot_sync(kFull, w0 || w1 || w2 || w3)) >= TC_DENSE_LANES) {
+            if (__any_sync(kFull, w0)) { if (w0) l_scan += chunk_mass(k0, xx, c0, a2); }
+            if (__any_sync(kFull, w1)) { if (w1) l_scan += chunk_mass(k1, xx, c0, a2); }
+            if (__any_sync(kFull, w2)) { if (w2) l_scan += chunk_mass(k2, xx, c0, a2); }
+            if (__any_sync(kFull, w3)) { if (w3) l_scan += chunk_mass(k3, xx, c0, a2); }
+            s0 = s0 && !w0; s1 = s1 && !w1; s2 = s2 && !w2; s3 = s3 && !w3;      // only candidate chunks go to the consumer
+        }
+    }
     push_chunk(k0, col0, s0, rg, lane, lanes_below);
     push_chunk(k1, col0 + TC_CHUNK, s1, rg, lane, lanes_below);
     push_chunk(k2, col0 + 2 * TC_CHUNK, s2, rg, lane, lanes_below);
@@ -326,8 +358,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // lists and row state are indexed by  li = column half * 128 + CTA-local row  (a row has one list per column half of the tile)
     float* lkeys = reinterpret_cast<float*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][16] list keys (16-byte aligned rows)
     int* lidx = reinterpret_cast<int*>(lkeys + TC_BM * LIST_STRIDE);                    // [256][16] list column indices
-    float* thr_hi_s = reinterpret_cast<float*>(lidx + TC_BM * LIST_STRIDE);             // [256] bound read by the scanners
-    float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
+    float2* thr2_s = reinterpret_cast<float2*>(lidx + TC_BM * LIST_STRIDE);             // [256] bounds read by the scanners: (list bound, softmax-window bound)
+    float* thr_list_s = reinterpret_cast<float*>(thr2_s + TC_BM);                       // [256] consumer-private row state from here on
     float* thr_mass_s = thr_list_s + TC_BM;
     float* kr_s = thr_mass_s + TC_BM;                     // smallest key seen (tightens the softmax window)
     float* r_s = kr_s + TC_BM;                            // reference distance of the row's mass: starts at the priming pass' sampled minimum
@@ -388,7 +420,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
         thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = 0.f; xx_s[rl] = xx;
         worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
-        thr_hi_s[rl] = (p.debug & 1) ? -INFINITY : (kSoft ? fmaxf(thl, thm) : thl);
+        thr2_s[rl] = (p.debug & 1) ? make_float2(-INFINITY, -INFINITY) : make_float2(thl, kSoft ? thm : -INFINITY);
     }
     if (warp == 1) {                        // TMEM of the pair: 512 columns per CTA (2 accumulator stages x 256), same warp in both CTAs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
@@ -471,7 +503,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int cgp = ew >> 2;                           // column group: columns cgp*64 .. +63 of each 256-column tile
         const int ch = cgp >> 1;                           // column half: the list / consumer this warp feeds
         const int cq = ch * 4 + quarter;                   // consumer / queue of this warp's (rows, column half)
-        const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 4u;
+        const uint32_t thr2_a = smem_u32(thr2_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 8u;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
         ScanRing rg;
         rg.base = smem_u32(q_mem) + (uint32_t)(cq * Q_CAP + (cgp & 1) * Q_SUB) * Q_ENTRY;   // this warp's own ring
@@ -485,6 +517,12 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         int col0 = tile0 * TC_BN + cgp * 64;
         const int col_step = p.tile_stride * TC_BN;
         uint32_t aph = 0;
+        // dense-window mode: private softmax accumulator of this thread's (row, column group), reference r0 (priming pass)
+        float l_scan = 0.f;
+        const float sc_xx = xx_s[ch * TC_SUB + quarter * 32 + lane];
+        float sc_c0 = 0.f;
+        if (kSoft && !kPrime && row0 + quarter * 32 + lane < p.N)
+            sc_c0 = p.a2 * sqrtf(fmaxf(__uint_as_float(__ldcg(p.rmin_global + (size_t)b * p.N + row0 + quarter * 32 + lane)), 0.f));
         // one tile: wait for the accumulator stage, pull this thread's 64 columns into registers (four TMEM loads in flight,
         // one wait), hand the stage back at once, then scan
         auto tile = [&](const int acc) {
@@ -496,7 +534,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_issue(taddr + TC_CHUNK, k1);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, k2);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, k3);
-            const float th = kPrime ? 0.f : lds_f32(thr_hi_a);      // the row's published bound: one read per tile
+            const float2 thr = kPrime ? make_float2(0.f, 0.f) : lds_v2(thr2_a);      // the row's published bounds: one read per tile
             tc_ld16_wait(k0);
             tc_ld16_after_wait(k1); tc_ld16_after_wait(k2); tc_ld16_after_wait(k3);
             tc_fence_before();
@@ -507,7 +545,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             } else if (p.debug & 2) {
                 if (k0[0] + k1[1] + k2[2] + k3[3] == 12345.678f) pl[0] = 0.f;      // keep the loads alive
             } else {
-                scan_tile(k0, k1, k2, k3, col0, th, rg, lane, lanes_below);
+                scan_tile<kSoft>(k0, k1, k2, k3, col0, thr, rg, lane, lanes_below, sc_xx, sc_c0, p.a2, l_scan);
                 if (rg.pub != rg.tail) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }     // once per tile
             }
             col0 += col_step;
@@ -515,6 +553,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll 1
         for (int it = 0; it + 1 < ntiles; it += 2) { tile(0); tile(1); aph ^= 1u; }
         if (ntiles & 1) tile(0);
+        if (kSoft && !kPrime)                                // all MMAs have retired: the X block is free.  [4 column groups][128 rows]
+            reinterpret_cast<float*>(Xs)[cgp * TC_SUB + quarter * 32 + lane] = l_scan;
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
             float* L = lkeys + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
 #pragma unroll
@@ -682,7 +722,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 if (mine) {
                     thl = fminf(thl, worst);
                     thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = l; worst_s[rl] = worst;
-                    *reinterpret_cast<volatile float*>(thr_hi_s + rl) = kSoft ? fmaxf(thl, thm) : thl;
+                    sts_v2(smem_u32(thr2_s + rl), thl, kSoft ? thm : -INFINITY);          // one 8-byte store: the scanners read a consistent pair
                     if (!kPrime && p.multi_split && changed && worst < LIST_EMPTY)
                         atomicMin(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)), __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
                     todo = false;
@@ -727,8 +767,19 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                         p.cb.idx[base + t] = has ? lidx[rl * LIST_STRIDE + t] : -1;
                     }
                     const float thl = thr_list_s[rl];
-                    p.cb.l[g_row * p.cb.P + part] = l_s[rl];
-                    p.cb.r[g_row * p.cb.P + part] = r_s[rl];
+                    float l_out = l_s[rl];
+                    const float r_out = r_s[rl];
+                    if (kSoft) {
+                        // mass the scanners of this column half summed themselves (dense-window mode), reference r0 >= r_out
+                        const float* lsc = reinterpret_cast<const float*>(Xs) + (cw >> 2) * 2 * TC_SUB + (rl & (TC_SUB - 1));
+                        const float ls = lsc[0] + lsc[TC_SUB];
+                        if (ls != 0.f) {
+                            const float r0 = sqrtf(fmaxf(__uint_as_float(__ldcg(p.rmin_global + g_row)), 0.f));
+                            l_out += ls * ex2_approx(-p.a2 * (r0 - r_out));
+                        }
+                    }
+                    p.cb.l[g_row * p.cb.P + part] = l_out;
+                    p.cb.r[g_row * p.cb.P + part] = r_out;
                     // discard bound of this list (true domain): everything it dropped has a key >= thr_list
                     p.cb.t[g_row * p.cb.P + part] = thl >= LIST_EMPTY ? INFINITY : fmaxf(fmaf(2.f, thl, xx), 0.f);
                 }
@@ -870,7 +921,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     DVM_LAUNCH_CHECK();
 
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
-    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 8 * TC_BM * sizeof(float)
+    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 9 * TC_BM * sizeof(float)
                         + TC_CONS_WARPS * sizeof(QCtl) + 128;
     auto kern = soft ? softmap_cand_tc_kernel<true, false> : softmap_cand_tc_kernel<false, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
