@@ -305,28 +305,30 @@ constexpr int TC_DENSE_LANES = 8;      // lanes of a warp with in-window non-can
 
 // one tile of one scanner thread: its row x 64 columns.  Four min-trees (8 three-input min instructions each), ONE vote for
 // the common "nothing below the bounds" case, then a vote + push per chunk.  thr = (list bound, softmax-window bound) of the row.
-// Dense-window mode (kSoft): when many lanes of the warp hold chunks that lie inside their row's softmax window but cannot be
-// list candidates (small alpha: every chunk of every row), pushing them through the queues would make the consumers the
-// bottleneck (22-140 TFLOP/s at alpha = 10); the lanes then add the 16 terms of such a chunk to a private accumulator
-// (fixed reference r0 of the priming pass, merged with the consumers' mass at the end) and only candidate chunks are pushed.
-template <bool kSoft>
+// Dense-window mode (kDense; chosen ONCE per warp from the priming pass: rows whose list threshold -- rank ~80 of the row --
+// already lies inside the softmax window have more in-window columns than the queues can carry; small alpha makes every row
+// such a row): pushing those chunks through the queues makes the consumers the bottleneck (22-140 TFLOP/s at alpha = 10), so
+// the lanes add the 16 terms of an in-window chunk without candidates to a private accumulator (fixed reference r0 of the
+// priming pass, merged with the consumers' mass at the end) and only candidate chunks are pushed.  A per-tile decision cost
+// ~20 instructions per warp and tile -- 10 % of the sweep at alpha = 100, where no warp needs the mode.
+template <bool kDense>
 __device__ __forceinline__ void scan_tile(const float (&k0)[TC_CHUNK], const float (&k1)[TC_CHUNK], const float (&k2)[TC_CHUNK],
                                           const float (&k3)[TC_CHUNK], int col0, float2 thr, ScanRing& rg, int lane, unsigned lanes_below,
-                                          float xx, float c0, float a2, float& l_scan) {
+                                          uint32_t xx_a, uint32_t c0_a, float a2, float& l_scan) {
     const float c_0 = min16(k0), c_1 = min16(k1), c_2 = min16(k2), c_3 = min16(k3);
-    const float th = kSoft ? fmaxf(thr.x, thr.y) : thr.x;
+    const float th = fmaxf(thr.x, thr.y);                     // hard mode publishes thr.y = -inf
     bool s0 = c_0 < th, s1 = c_1 < th, s2 = c_2 < th, s3 = c_3 < th;
     if (!__any_sync(kFull, s0 || s1 || s2 || s3)) return;
-    if (kSoft) {
-        // in-window chunks that hold no list candidate
+    if (kDense) {
+        // in-window chunks that hold no list candidate: their 16 terms are summed here, only candidate chunks are pushed
         const bool w0 = s0 && c_0 >= thr.x, w1 = s1 && c_1 >= thr.x, w2 = s2 && c_2 >= thr.x, w3 = s3 && c_3 >= thr.x;
-        if (__popc(__ballot_sync(kFull, w0 || w1 || w2 || w3)) >= TC_DENSE_LANES) {
-            if (__any_sync(kFull, w0)) { if (w0) l_scan += chunk_mass(k0, xx, c0, a2); }
-            if (__any_sync(kFull, w1)) { if (w1) l_scan += chunk_mass(k1, xx, c0, a2); }
-            if (__any_sync(kFull, w2)) { if (w2) l_scan += chunk_mass(k2, xx, c0, a2); }
-            if (__any_sync(kFull, w3)) { if (w3) l_scan += chunk_mass(k3, xx, c0, a2); }
-            s0 = s0 && !w0; s1 = s1 && !w1; s2 = s2 && !w2; s3 = s3 && !w3;      // only candidate chunks go to the consumer
-        }
+        const float xx = lds_f32(xx_a), c0 = lds_f32(c0_a);
+        if (__any_sync(kFull, w0)) { if (w0) l_scan += chunk_mass(k0, xx, c0, a2); }
+        if (__any_sync(kFull, w1)) { if (w1) l_scan += chunk_mass(k1, xx, c0, a2); }
+        if (__any_sync(kFull, w2)) { if (w2) l_scan += chunk_mass(k2, xx, c0, a2); }
+        if (__any_sync(kFull, w3)) { if (w3) l_scan += chunk_mass(k3, xx, c0, a2); }
+        s0 = s0 && !w0; s1 = s1 && !w1; s2 = s2 && !w2; s3 = s3 && !w3;
+        if (!__any_sync(kFull, s0 || s1 || s2 || s3)) return;
     }
     push_chunk(k0, col0, s0, rg, lane, lanes_below);
     push_chunk(k1, col0 + TC_CHUNK, s1, rg, lane, lanes_below);
@@ -366,7 +368,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     float* l_s = r_s + TC_BM;                             // sum of exp2(-a2 (d - r)) over the non-candidate columns
     float* xx_s = l_s + TC_BM;                            // [256] |x~|^2
     float* worst_s = xx_s + TC_BM;                        // [256] largest key of the row's list (slot number in its low bits)
-    QCtl* qctl = reinterpret_cast<QCtl*>(worst_s + TC_BM);   // [TC_CONS_WARPS]
+    float* c0_s = worst_s + TC_BM;                        // [128] a2 * r0 per row (r0 = priming pass' sampled minimum): dense-window reference
+    QCtl* qctl = reinterpret_cast<QCtl*>(c0_s + TC_SUB);     // [TC_CONS_WARPS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(qctl + TC_CONS_WARPS);
     uint64_t* full = bars;                 // [NST]   leader's copy is used: expect_tx covers the TMA of BOTH CTAs
     uint64_t* empty = bars + TC_NST;       // [NST]   per CTA, signalled by the leader's multicast commit
@@ -419,6 +422,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             }
         }
         thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = 0.f; xx_s[rl] = xx;
+        if (rl < TC_SUB) c0_s[rl] = p.a2 * r;
         worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
         thr2_s[rl] = (p.debug & 1) ? make_float2(-INFINITY, -INFINITY) : make_float2(thl, kSoft ? thm : -INFINITY);
     }
@@ -519,10 +523,12 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         uint32_t aph = 0;
         // dense-window mode: private softmax accumulator of this thread's (row, column group), reference r0 (priming pass)
         float l_scan = 0.f;
-        const float sc_xx = xx_s[ch * TC_SUB + quarter * 32 + lane];
-        float sc_c0 = 0.f;
-        if (kSoft && !kPrime && row0 + quarter * 32 + lane < p.N)
-            sc_c0 = p.a2 * sqrtf(fmaxf(__uint_as_float(__ldcg(p.rmin_global + (size_t)b * p.N + row0 + quarter * 32 + lane)), 0.f));
+        const uint32_t sc_xx_a = smem_u32(xx_s + quarter * 32 + lane), sc_c0_a = smem_u32(c0_s + quarter * 32 + lane);
+        bool dense_warp = false;
+        if (kSoft && !kPrime) {
+            const float2 t0 = lds_v2(thr2_a);                  // initial bounds: list threshold of the priming pass, window around its minimum
+            dense_warp = __popc(__ballot_sync(kFull, t0.x < t0.y)) >= TC_DENSE_LANES;
+        }
         // one tile: wait for the accumulator stage, pull this thread's 64 columns into registers (four TMEM loads in flight,
         // one wait), hand the stage back at once, then scan
         auto tile = [&](const int acc) {
@@ -545,7 +551,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             } else if (p.debug & 2) {
                 if (k0[0] + k1[1] + k2[2] + k3[3] == 12345.678f) pl[0] = 0.f;      // keep the loads alive
             } else {
-                scan_tile<kSoft>(k0, k1, k2, k3, col0, thr, rg, lane, lanes_below, sc_xx, sc_c0, p.a2, l_scan);
+                if (kSoft && dense_warp) scan_tile<true>(k0, k1, k2, k3, col0, thr, rg, lane, lanes_below, sc_xx_a, sc_c0_a, p.a2, l_scan);
+                else scan_tile<false>(k0, k1, k2, k3, col0, thr, rg, lane, lanes_below, sc_xx_a, sc_c0_a, p.a2, l_scan);
                 if (rg.pub != rg.tail) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }     // once per tile
             }
             col0 += col_step;
@@ -921,7 +928,7 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     DVM_LAUNCH_CHECK();
 
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
-    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 9 * TC_BM * sizeof(float)
+    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 9 * TC_BM * sizeof(float) + TC_SUB * sizeof(float)
                         + TC_CONS_WARPS * sizeof(QCtl) + 128;
     auto kern = soft ? softmap_cand_tc_kernel<true, false> : softmap_cand_tc_kernel<false, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
