@@ -49,6 +49,7 @@ constexpr int TC_CHUNK = 16;               // columns per min-tree
 constexpr int TC_PRIME_STRIDE = 10;        // priming pass: every 10th tile.  Measured at 4 x 50k x 50k (prime + sweep, ms): stride 16: 3.24,
                                            // 12: 3.18, 10: 3.155, 8: 3.15; <= 6: thresholds so tight that rows run out of candidates (slow path)
 constexpr int TC_PRIME_MIN_TILES = 16;      // ... when the sweep has at least this many tiles (M >= 4k): below, the sample is too small
+constexpr float TC_DENSE_ALPHA = 40.f;      // soft maps with alpha below this run the dense-window instance of the sweep
 constexpr int TC_PREP_ROWS = 32;           // rows per block of the operand preparation (8 warps x 4 rows)     // ... when the sweep has at least this many tiles (M >= 16k)
 
 
@@ -292,36 +293,40 @@ __device__ __forceinline__ void push_chunk(const float (&k)[TC_CHUNK], int cbase
 
 // softmax terms of one chunk against the fixed per-row reference (c0 = a2 * r0): exp2(c0 - a2 d), d = sqrt(2 key + |x~|^2)
 __device__ __forceinline__ float chunk_mass(const float (&k)[TC_CHUNK], float xx, float c0, float a2) {
-    float s0 = 0.f, s1 = 0.f;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int t = 0; t < TC_CHUNK; t += 2) {
-        s0 += ex2_approx(fmaf(-a2, key_dist_fast(k[t], xx), c0));
-        s1 += ex2_approx(fmaf(-a2, key_dist_fast(k[t + 1], xx), c0));
+    for (int t = 0; t < TC_CHUNK; t += 4) {                       // four independent MUFU chains in flight
+        float x[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = fmaxf(fmaf(2.f, k[t + u], xx), 1e-30f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r[u]) : "f"(x[u]));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] += ex2_approx(fmaf(-a2 * x[u], r[u], c0));
     }
-    return s0 + s1;
+    return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
-constexpr int TC_DENSE_LANES = 8;      // lanes of a warp with in-window non-candidate chunks from which the warp sums them itself
 
 // one tile of one scanner thread: its row x 64 columns.  Four min-trees (8 three-input min instructions each), ONE vote for
 // the common "nothing below the bounds" case, then a vote + push per chunk.  thr = (list bound, softmax-window bound) of the row.
-// Dense-window mode (kDense; chosen ONCE per warp from the priming pass: rows whose list threshold -- rank ~80 of the row --
-// already lies inside the softmax window have more in-window columns than the queues can carry; small alpha makes every row
-// such a row): pushing those chunks through the queues makes the consumers the bottleneck (22-140 TFLOP/s at alpha = 10), so
-// the lanes add the 16 terms of an in-window chunk without candidates to a private accumulator (fixed reference r0 of the
-// priming pass, merged with the consumers' mass at the end) and only candidate chunks are pushed.  A per-tile decision cost
-// ~20 instructions per warp and tile -- 10 % of the sweep at alpha = 100, where no warp needs the mode.
+// Dense-window mode (kDense, a separate kernel instance the host selects for small alpha, where every chunk of every row lies
+// inside the softmax window): pushing those chunks through the queues makes the consumers the bottleneck (22-140 TFLOP/s at
+// alpha = 10), so the lanes add the 16 terms of an in-window chunk without candidates to a private accumulator (fixed
+// reference r0 of the priming pass, merged with the consumers' mass at the end) and only candidate chunks are pushed.
+// Measured alternatives: a per-tile decision costs ~20 instructions per warp and tile (10 % of the sweep at alpha = 100); a
+// per-warp decision from the priming pass turns the mode on for most warps of a peaked 50k problem (the rank-80 list threshold
+// lies inside the window there) and halves its speed -- the queues are the better path whenever they keep up.
 template <bool kDense>
 __device__ __forceinline__ void scan_tile(const float (&k0)[TC_CHUNK], const float (&k1)[TC_CHUNK], const float (&k2)[TC_CHUNK],
-                                          const float (&k3)[TC_CHUNK], int col0, float2 thr, ScanRing& rg, int lane, unsigned lanes_below,
+                                          const float (&k3)[TC_CHUNK], int col0, float th, float thl, ScanRing& rg, int lane, unsigned lanes_below,
                                           uint32_t xx_a, uint32_t c0_a, float a2, float& l_scan) {
     const float c_0 = min16(k0), c_1 = min16(k1), c_2 = min16(k2), c_3 = min16(k3);
-    const float th = fmaxf(thr.x, thr.y);                     // hard mode publishes thr.y = -inf
     bool s0 = c_0 < th, s1 = c_1 < th, s2 = c_2 < th, s3 = c_3 < th;
     if (!__any_sync(kFull, s0 || s1 || s2 || s3)) return;
     if (kDense) {
         // in-window chunks that hold no list candidate: their 16 terms are summed here, only candidate chunks are pushed
-        const bool w0 = s0 && c_0 >= thr.x, w1 = s1 && c_1 >= thr.x, w2 = s2 && c_2 >= thr.x, w3 = s3 && c_3 >= thr.x;
+        const bool w0 = s0 && c_0 >= thl, w1 = s1 && c_1 >= thl, w2 = s2 && c_2 >= thl, w3 = s3 && c_3 >= thl;
         const float xx = lds_f32(xx_a), c0 = lds_f32(c0_a);
         if (__any_sync(kFull, w0)) { if (w0) l_scan += chunk_mass(k0, xx, c0, a2); }
         if (__any_sync(kFull, w1)) { if (w1) l_scan += chunk_mass(k1, xx, c0, a2); }
@@ -347,7 +352,7 @@ __device__ __forceinline__ void prime_chunk(const float (&k)[TC_CHUNK], float (&
 }
 
 // kPrime: priming pass -- strided tile sample, hard mode, only outputs are thr_global / rmin_global.
-template <bool kSoft, bool kPrime>
+template <bool kSoft, bool kPrime, bool kDense = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXe,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYe, const TcParams p) {
@@ -360,7 +365,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // lists and row state are indexed by  li = column half * 128 + CTA-local row  (a row has one list per column half of the tile)
     float* lkeys = reinterpret_cast<float*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][16] list keys (16-byte aligned rows)
     int* lidx = reinterpret_cast<int*>(lkeys + TC_BM * LIST_STRIDE);                    // [256][16] list column indices
-    float2* thr2_s = reinterpret_cast<float2*>(lidx + TC_BM * LIST_STRIDE);             // [256] bounds read by the scanners: (list bound, softmax-window bound)
+    float2* thr2_s = reinterpret_cast<float2*>(lidx + TC_BM * LIST_STRIDE);             // [256] bounds read by the scanners: (max(list bound, softmax-window bound), list bound)
     float* thr_list_s = reinterpret_cast<float*>(thr2_s + TC_BM);                       // [256] consumer-private row state from here on
     float* thr_mass_s = thr_list_s + TC_BM;
     float* kr_s = thr_mass_s + TC_BM;                     // smallest key seen (tightens the softmax window)
@@ -424,7 +429,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = 0.f; xx_s[rl] = xx;
         if (rl < TC_SUB) c0_s[rl] = p.a2 * r;
         worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
-        thr2_s[rl] = (p.debug & 1) ? make_float2(-INFINITY, -INFINITY) : make_float2(thl, kSoft ? thm : -INFINITY);
+        thr2_s[rl] = (p.debug & 1) ? make_float2(-INFINITY, -INFINITY) : make_float2(kSoft ? fmaxf(thl, thm) : thl, thl);
     }
     if (warp == 1) {                        // TMEM of the pair: 512 columns per CTA (2 accumulator stages x 256), same warp in both CTAs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
@@ -524,11 +529,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         // dense-window mode: private softmax accumulator of this thread's (row, column group), reference r0 (priming pass)
         float l_scan = 0.f;
         const uint32_t sc_xx_a = smem_u32(xx_s + quarter * 32 + lane), sc_c0_a = smem_u32(c0_s + quarter * 32 + lane);
-        bool dense_warp = false;
-        if (kSoft && !kPrime) {
-            const float2 t0 = lds_v2(thr2_a);                  // initial bounds: list threshold of the priming pass, window around its minimum
-            dense_warp = __popc(__ballot_sync(kFull, t0.x < t0.y)) >= TC_DENSE_LANES;
-        }
+
         // one tile: wait for the accumulator stage, pull this thread's 64 columns into registers (four TMEM loads in flight,
         // one wait), hand the stage back at once, then scan
         auto tile = [&](const int acc) {
@@ -540,7 +541,11 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tc_ld16_issue(taddr + TC_CHUNK, k1);
             tc_ld16_issue(taddr + 2 * TC_CHUNK, k2);
             tc_ld16_issue(taddr + 3 * TC_CHUNK, k3);
-            const float2 thr = kPrime ? make_float2(0.f, 0.f) : lds_v2(thr2_a);      // the row's published bounds: one read per tile
+            float th = 0.f, thl = 0.f;                               // the row's published bounds: one read per tile
+            if (!kPrime) {
+                if (kDense) { const float2 t2 = lds_v2(thr2_a); th = t2.x; thl = t2.y; }
+                else th = lds_f32(thr2_a);
+            }
             tc_ld16_wait(k0);
             tc_ld16_after_wait(k1); tc_ld16_after_wait(k2); tc_ld16_after_wait(k3);
             tc_fence_before();
@@ -551,8 +556,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             } else if (p.debug & 2) {
                 if (k0[0] + k1[1] + k2[2] + k3[3] == 12345.678f) pl[0] = 0.f;      // keep the loads alive
             } else {
-                if (kSoft && dense_warp) scan_tile<true>(k0, k1, k2, k3, col0, thr, rg, lane, lanes_below, sc_xx_a, sc_c0_a, p.a2, l_scan);
-                else scan_tile<false>(k0, k1, k2, k3, col0, thr, rg, lane, lanes_below, sc_xx_a, sc_c0_a, p.a2, l_scan);
+                scan_tile<kDense>(k0, k1, k2, k3, col0, th, thl, rg, lane, lanes_below, sc_xx_a, sc_c0_a, p.a2, l_scan);
                 if (rg.pub != rg.tail) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }     // once per tile
             }
             col0 += col_step;
@@ -560,7 +564,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll 1
         for (int it = 0; it + 1 < ntiles; it += 2) { tile(0); tile(1); aph ^= 1u; }
         if (ntiles & 1) tile(0);
-        if (kSoft && !kPrime)                                // all MMAs have retired: the X block is free.  [4 column groups][128 rows]
+        if (kDense)                                          // all MMAs have retired: the X block is free.  [4 column groups][128 rows]
             reinterpret_cast<float*>(Xs)[cgp * TC_SUB + quarter * 32 + lane] = l_scan;
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
             float* L = lkeys + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
@@ -729,7 +733,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 if (mine) {
                     thl = fminf(thl, worst);
                     thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = l; worst_s[rl] = worst;
-                    sts_v2(smem_u32(thr2_s + rl), thl, kSoft ? thm : -INFINITY);          // one 8-byte store: the scanners read a consistent pair
+                    sts_v2(smem_u32(thr2_s + rl), kSoft ? fmaxf(thl, thm) : thl, thl);    // one 8-byte store: (bound, list bound) stay a consistent pair
                     if (!kPrime && p.multi_split && changed && worst < LIST_EMPTY)
                         atomicMin(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)), __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
                     todo = false;
@@ -776,7 +780,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const float thl = thr_list_s[rl];
                     float l_out = l_s[rl];
                     const float r_out = r_s[rl];
-                    if (kSoft) {
+                    if (kDense) {
                         // mass the scanners of this column half summed themselves (dense-window mode), reference r0 >= r_out
                         const float* lsc = reinterpret_cast<const float*>(Xs) + (cw >> 2) * 2 * TC_SUB + (rl & (TC_SUB - 1));
                         const float ls = lsc[0] + lsc[TC_SUB];
@@ -930,11 +934,15 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
     const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 9 * TC_BM * sizeof(float) + TC_SUB * sizeof(float)
                         + TC_CONS_WARPS * sizeof(QCtl) + 128;
-    auto kern = soft ? softmap_cand_tc_kernel<true, false> : softmap_cand_tc_kernel<false, false>;
+    // dense-window instance for small alpha (every chunk inside the softmax window): crossover measured between alpha = 10
+    // (141 -> 290 TFLOP/s at 50k) and alpha = 100 (810 -> 390 when forced)
+    const bool dense = soft && alpha < TC_DENSE_ALPHA;
+    auto kern = !soft ? softmap_cand_tc_kernel<false, false> : dense ? softmap_cand_tc_kernel<true, false, true> : softmap_cand_tc_kernel<true, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
     static bool attr_done = false;
     if (!attr_done) {
         DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(kprime, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
