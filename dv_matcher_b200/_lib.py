@@ -11,7 +11,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvm_b200.so")
+# DVM_LIB_PATH: A/B experiments against another build of the same C ABI (tools/); symbols it lacks are skipped
+LIB_PATH = os.environ.get("DVM_LIB_PATH") or os.path.join(_HERE, "libdvm_b200.so")
 
 c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 
@@ -78,6 +79,8 @@ def load():
                     "(nvcc, sm_100a). dv_matcher_b200 has no CPU or PyTorch fallback.")
             lib = ctypes.CDLL(LIB_PATH)
             for name, (res, args) in SIGNATURES.items():
+                if os.environ.get("DVM_LIB_PATH") and not hasattr(lib, name):
+                    continue
                 fn = getattr(lib, name)      # AttributeError here == header/library mismatch
                 fn.restype = res
                 fn.argtypes = args

@@ -15,13 +15,9 @@
 // (0.5-1 instruction per entry) decides whether any entry of the chunk can matter (a top-16 candidate or a
 // term inside the softmax window); only those chunks take the slow path.
 //
-// Warp roles (896 threads per CTA = 7 warpgroups): warpgroup 0 = warp 0 TMA producer, warp 1 TMEM owner (+ MMA issuer, one lane,
-// leader CTA), warps 2-3 idle; warpgroups 1-4 (warps 4..19) = scanners: TMEM lane quarter = warp % 4 (hardware rule), column
-// group = (warp - 4) / 4: one thread = one row x 64 columns of every tile; warpgroups 5-6 (warps 20..27) = consumers (32 rows x
-// column half of the tile each).  Registers are redistributed after the prologue (setmaxnreg): warpgroup 0 keeps 40, the
-// consumers 56, the scanners take 88 -- enough to pull their whole 64-column slice of the accumulator into registers with four
-// tcgen05.ld in flight and hand the TMEM stage back BEFORE any data-dependent work (min-trees, queue pushes, ring-full waits).
-// The MMA of tile t+2 therefore never waits for the slowest scanner's push path, only for the TMEM read of tile t.
+// Warp roles (832 threads per CTA): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer, one lane, leader CTA),
+// warps 2..17 = scanners: TMEM lane quarter = warp % 4 (hardware rule), column group = (warp - 2) / 4: one thread = one
+// row x 64 columns of every tile; warps 18..25 = consumers (32 rows x column half of the tile each).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> scanners), all mbarriers, signalled across the
 // pair by multicast commits / remote arrives; no CTA-wide barrier inside the sweep.
 #include <cuda.h>
@@ -38,9 +34,7 @@ constexpr int TC_KBLK = 64;           // 16-bit elements per 128-byte swizzle ro
 constexpr int TC_KEXT = 16;           // extra K block: norm columns (one UMMA K step), 32-byte swizzle rows
 constexpr int TC_SCAN_WARPS = 16;      // epilogue scanners
 constexpr int TC_CONS_WARPS = 8;       // epilogue consumers (one per 32 rows x column half of the tile)
-constexpr int TC_LEAD_WARPS = 4;       // warpgroup 0: TMA producer, MMA issuer, two idle warps (setmaxnreg works on whole warpgroups)
-constexpr int TC_THREADS = 32 * (TC_LEAD_WARPS + TC_SCAN_WARPS + TC_CONS_WARPS);     // 896 = 7 warpgroups
-constexpr int TC_REGS_LEAD = 40, TC_REGS_SCAN = 88, TC_REGS_CONS = 56;              // 128*40 + 512*88 + 256*56 = 64512 = 72*896 (the launch allocation)
+constexpr int TC_THREADS = 64 + 32 * (TC_SCAN_WARPS + TC_CONS_WARPS);
 constexpr int TC_NST = 3;             // Y ring depth
 constexpr int TC_BLK_BYTES = 128 * 128;        // one 128-row x 64-element K block
 constexpr int TC_EXT_BYTES = 128 * 32;         // one 128-row x 16-element K block
@@ -157,10 +151,6 @@ struct TcParams {
     int tiles_total, tiles_per_split;
     int tile_stride;             // 1 for the sweep; > 1: the priming pass visits every tile_stride-th tile only
     int multi_split;             // column-split CTAs exchange thresholds through thr_global during the sweep
-    int debug;                   // DVM_TC_DEBUG experiment switches (0 in production): 1 = scanners never push, 2 = scanners only drain
-                                 // TMEM (no min-tree), 4 = accumulator wait without nanosleep back-off, 8 = consumers discard entries
-    int prime_thr;               // priming pass: also publish the list threshold (0 for small problems: the sample is too small
-                                 // for its 8th smallest chunk minimum to leave 16 candidates below it -- only the softmax reference)
     float a2, cut_over_alpha;
     uint32_t idesc;
     const float* xx;             // [B*N]
@@ -180,20 +170,12 @@ struct TcParams {
 // independent of the data.
 //
 // 8 consumer warps (one per 32 rows x column half of the tile: a row has one list per column half) drain the rings of
-// their two scanner warps with ONE LANE PER ENTRY (full lane utilisation whatever the rows are).  An entry's keys are split
-// against ONE snapshot of the row's list bound `lim`:
-//   * keys >= lim can never become candidates (bounds only tighten): their softmax terms exp2(c0 - a2 d) are summed by the
-//     lane at once, relative to the row's CURRENT reference distance r (read with the snapshot; it only moves in the
-//     serialised path below, which runs after these sums have been added): the terms of different entries of a row are
-//     independent, so same-row lanes of a batch are pre-reduced with shuffles and the first of them adds the sum to the
-//     row's accumulator -- no serialisation, however many entries a row with a wide softmax window pushes (such rows used
-//     to serialise the whole batch: up to 16 passes of the list code per batch);
-//   * keys < lim are list candidates: only these take the serialised path (same-row entries one after the other, in queue
-//     order): the key replaces the worst entry of the row's K-entry list in shared memory, what it evicts (or the key itself
-//     if the bound has tightened meanwhile) adds its term to the row's mass; the lane then publishes the row's new bound
-//     thr_hi = max(list threshold, softmax-window bound).
-// Every scanner warp owns a single-producer ring (tail in a register, no atomic) and publishes its entries with one fence +
-// tail store per tile; it waits for space only after publishing what it holds, the consumer never waits for a producer, so
+// their two scanner warps with ONE LANE PER ENTRY (full lane utilisation whatever the rows are): the entry's keys below
+// the bound replace the worst entry of the row's K-entry list (shared memory) or add their softmax term
+// exp2(-a2 (d - r)) to the row's mass; the lane then publishes the row's new bound thr_hi = max(list threshold,
+// softmax-window bound).  Entries of the same row inside one batch are serialised (__match_any_sync).  Every scanner
+// warp owns a single-producer ring (tail in a register, no atomic) and publishes its entries with one fence + tail
+// store per tile; it waits for space only after publishing what it holds, the consumer never waits for a producer, so
 // the protocol cannot deadlock.
 //
 // The list threshold of a row starts from the PRIMING pass (8th smallest chunk minimum of a 1/10 column sample ~ rank 80) and
@@ -204,7 +186,7 @@ constexpr int KP = 8;                  // list length of the priming pass
 constexpr int Q_CAP = 64;              // queue slots per consumer: two single-producer rings of Q_SUB slots
 constexpr int Q_SUB = Q_CAP / 2;       // one ring per scanner warp feeding the consumer
 constexpr int Q_ENTRY = 80;            // bytes: 16 keys | row, first column | sequence word, pad
-constexpr int LIST_STRIDE = KC;        // a list = 16 keys (64 B, read back as four 16-byte loads) + 16 column indices, in two arrays
+constexpr int LIST_STRIDE = KC + 1;    // float2 per row (odd stride in 8-byte units: conflict-poor)
 constexpr float LIST_EMPTY = 3.0e38f;  // "no entry" key (finite, so that a slot number can live in its low mantissa bits)
 
 struct QCtl { unsigned head0, head1, tail0, tail1, done, pad0, pad1, pad2; };   // ring heads (consumer writes), published tails
@@ -215,12 +197,22 @@ __device__ __forceinline__ float key_dist_approx(float key, float xx) {        /
     const float x = fmaxf(fmaf(2.f, key, xx), 1e-30f);
     return x * __frsqrt_rn(x);
 }
-// d = sqrt(2 key + |x~|^2) with the MUFU reciprocal square root (2 ulp): only used for softmax terms of NON-candidate columns,
-// whose keys already carry the 16-bit operand rounding (orders of magnitude above 2 ulp)
-__device__ __forceinline__ float key_dist_fast(float key, float xx) {
-    const float x = fmaxf(fmaf(2.f, key, xx), 1e-30f);
-    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return x * r;
+// softmax terms of one chunk against a FIXED reference (c0 = a2 * r0): sum of exp2(c0 - a2 d), d = sqrt(2 key + |x~|^2), with the
+// MUFU reciprocal square root (2 ulp: these are non-candidate terms whose keys already carry the 16-bit operand rounding).
+// Four independent MUFU chains in flight.
+__device__ __forceinline__ float chunk_mass(const float (&k)[16], float xx, float c0, float a2) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 16; t += 4) {
+        float x[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = fmaxf(fmaf(2.f, k[t + u], xx), 1e-30f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r[u]) : "f"(x[u]));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] += ex2_approx(fmaf(-a2 * x[u], r[u], c0));
+    }
+    return (s[0] + s[1]) + (s[2] + s[3]);
 }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float min16(const float (&k)[16]) {                  // 8 three-input min instructions
@@ -243,102 +235,64 @@ __device__ __forceinline__ float max16(const float (&k)[16]) {
                  max3(max3(k[9], k[10], k[11]), max3(k[12], k[13], k[14]), k[15]));
 }
 
+// scanner: one 16-column chunk of one row.
+// kPrivBound (hard mode): while the consumer has not published a list threshold yet (first tile of a CTA that starts
+// without a primed threshold) the thread bounds it itself -- the largest key of any chunk it has seen is >= the row's
+// 16th smallest key -- so the start-up does not flood the queue with every chunk of every row.
 // makes the ring entries written so far by all lanes of the warp visible to the consumer: tail word at `tail_a`
 __device__ __forceinline__ void ring_publish(uint32_t tail_a, unsigned tail, int lane) {
     __syncwarp();                                                    // orders the lanes' entry stores before lane 0's release
     if (lane == 0) sts_u32_release(tail_a, tail);
 }
 
-// A scanner warp's single-producer ring: everything lives in (warp-uniform) registers; the consumer's head is re-read only when
-// the ring looks full.  Entries are PUBLISHED (one fence + the tail word) once per tile.
-struct ScanRing {
-    uint32_t base;           // shared-window address of slot 0
-    uint32_t head_a;         // ... of the consumer's head word; the published tail sits at head_a + 8
-    unsigned tail, head_seen, pub;
-};
+// kDense (dense-window instance, small alpha -- every chunk of every row lies inside the softmax window): pushing all those
+// chunks through the queues makes the consumers the bottleneck (22-91 TFLOP/s at alpha = 10), so a chunk that is inside the
+// window but holds no list candidate (chunk minimum >= the row's list bound) adds its 16 terms to the thread's PRIVATE
+// accumulator (fixed reference r0 of the priming pass; merged with the consumers' mass at the end) and only chunks with
+// candidates are pushed.  Any (possibly stale) pair of bounds is safe: a pushed chunk is settled completely by the consumer,
+// a chunk summed here has no key below the list bound it was compared with, hence none below the current one.
+struct DenseState { uint32_t thl_a; float xx, c0, a2; float l; };
 
-// rare: kept out of the scan loop, and by VALUE (a reference would pin the ring state to local memory)
-__device__ __noinline__ uint2 ring_wait_space(uint32_t head_a, unsigned tail, unsigned pub, int n, int lane) {
-    unsigned head_seen;
-    for (;;) {
-        if (pub != tail) { ring_publish(head_a + 8, tail, lane); pub = tail; }   // the consumer must see what it has to free
-        head_seen = lds_u32_volatile(head_a);
-        if ((int)(tail + (unsigned)n - head_seen) <= Q_SUB) break;
-        __nanosleep(20);
+template <bool kPrivBound, bool kDense>
+__device__ __forceinline__ void scan_chunk(const float (&k)[TC_CHUNK], int cbase, uint32_t thr_hi_a, uint32_t q_a, uint32_t head_a,
+                                           int row_in_q, int lane, float& priv, bool first_tile, unsigned& tail, unsigned& head_seen,
+                                           unsigned& pub, DenseState& ds) {
+    float th = lds_f32(thr_hi_a);
+    if (kPrivBound) {
+        th = fminf(th, priv);
+        if (first_tile) priv = fminf(priv, max16(k));
     }
-    return make_uint2(head_seen, pub);
-}
-
-// the lanes whose chunk can matter (`slow`) copy the WHOLE chunk (16 keys, row, first column) into the warp's ring
-__device__ __forceinline__ void push_chunk(const float (&k)[TC_CHUNK], int cbase, bool slow, ScanRing& rg, int lane, unsigned lanes_below) {
+    const float cmin = min16(k);
+    bool slow = cmin < th;
+    if (kDense) {
+        const bool win = slow && cmin >= lds_f32(ds.thl_a);          // inside the window, no candidate
+        if (__any_sync(kFull, win)) {
+            if (win) ds.l += chunk_mass(k, ds.xx, ds.c0, ds.a2);
+            slow = slow && !win;
+        }
+    }
     const unsigned mask = __ballot_sync(kFull, slow);
     if (mask == 0u) return;                                          // warp-uniform
+    // the ring has ONE producer (this warp): the tail is a warp-uniform register, no atomic; the consumer's head is
+    // re-read only when the ring looks full.  Entries are PUBLISHED (one fence + the tail word) once per tile, at a
+    // point where the warp has nothing in flight -- a release per entry drained the TMEM-load pipeline every time.
     const int n = __popc(mask);
-    if ((int)(rg.tail + (unsigned)n - rg.head_seen) > Q_SUB) {
-        const uint2 hp = ring_wait_space(rg.head_a, rg.tail, rg.pub, n, lane);
-        rg.head_seen = hp.x; rg.pub = hp.y;
+    while ((int)(tail + (unsigned)n - head_seen) > Q_SUB) {
+        if (pub != tail) { ring_publish(head_a + 8, tail, lane); pub = tail; }     // the consumer must see what it has to free
+        head_seen = lds_u32_volatile(head_a);
+        if ((int)(tail + (unsigned)n - head_seen) > Q_SUB) __nanosleep(20);
     }
     if (slow) {
-        const unsigned g = rg.tail + (unsigned)__popc(mask & lanes_below);
-        const uint32_t ea = rg.base + (g & (unsigned)(Q_SUB - 1)) * Q_ENTRY;
+        const unsigned g = tail + (unsigned)__popc(mask & ((1u << lane) - 1u));
+        const uint32_t ea = q_a + (g % Q_SUB) * Q_ENTRY;
         sts_v4(ea, k[0], k[1], k[2], k[3]);
         sts_v4(ea + 16, k[4], k[5], k[6], k[7]);
         sts_v4(ea + 32, k[8], k[9], k[10], k[11]);
         sts_v4(ea + 48, k[12], k[13], k[14], k[15]);
-        sts_v2(ea + 64, __int_as_float(lane), __int_as_float(cbase));
+        sts_v2(ea + 64, __int_as_float(row_in_q), __int_as_float(cbase));
     }
-    rg.tail += (unsigned)n;
-    if (n >= 8) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }   // flood (start-up, dense softmax windows): do not sit on the entries
-}
-
-// softmax terms of one chunk against the fixed per-row reference (c0 = a2 * r0): exp2(c0 - a2 d), d = sqrt(2 key + |x~|^2)
-__device__ __forceinline__ float chunk_mass(const float (&k)[TC_CHUNK], float xx, float c0, float a2) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int t = 0; t < TC_CHUNK; t += 4) {                       // four independent MUFU chains in flight
-        float x[4], r[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = fmaxf(fmaf(2.f, k[t + u], xx), 1e-30f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r[u]) : "f"(x[u]));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) s[u] += ex2_approx(fmaf(-a2 * x[u], r[u], c0));
-    }
-    return (s[0] + s[1]) + (s[2] + s[3]);
-}
-
-
-// one tile of one scanner thread: its row x 64 columns.  Four min-trees (8 three-input min instructions each), ONE vote for
-// the common "nothing below the bounds" case, then a vote + push per chunk.  thr = (list bound, softmax-window bound) of the row.
-// Dense-window mode (kDense, a separate kernel instance the host selects for small alpha, where every chunk of every row lies
-// inside the softmax window): pushing those chunks through the queues makes the consumers the bottleneck (22-140 TFLOP/s at
-// alpha = 10), so the lanes add the 16 terms of an in-window chunk without candidates to a private accumulator (fixed
-// reference r0 of the priming pass, merged with the consumers' mass at the end) and only candidate chunks are pushed.
-// Measured alternatives: a per-tile decision costs ~20 instructions per warp and tile (10 % of the sweep at alpha = 100); a
-// per-warp decision from the priming pass turns the mode on for most warps of a peaked 50k problem (the rank-80 list threshold
-// lies inside the window there) and halves its speed -- the queues are the better path whenever they keep up.
-template <bool kDense>
-__device__ __forceinline__ void scan_tile(const float (&k0)[TC_CHUNK], const float (&k1)[TC_CHUNK], const float (&k2)[TC_CHUNK],
-                                          const float (&k3)[TC_CHUNK], int col0, float th, float thl, ScanRing& rg, int lane, unsigned lanes_below,
-                                          uint32_t xx_a, uint32_t c0_a, float a2, float& l_scan) {
-    const float c_0 = min16(k0), c_1 = min16(k1), c_2 = min16(k2), c_3 = min16(k3);
-    bool s0 = c_0 < th, s1 = c_1 < th, s2 = c_2 < th, s3 = c_3 < th;
-    if (!__any_sync(kFull, s0 || s1 || s2 || s3)) return;
-    if (kDense) {
-        // in-window chunks that hold no list candidate: their 16 terms are summed here, only candidate chunks are pushed
-        const bool w0 = s0 && c_0 >= thl, w1 = s1 && c_1 >= thl, w2 = s2 && c_2 >= thl, w3 = s3 && c_3 >= thl;
-        const float xx = lds_f32(xx_a), c0 = lds_f32(c0_a);
-        if (__any_sync(kFull, w0)) { if (w0) l_scan += chunk_mass(k0, xx, c0, a2); }
-        if (__any_sync(kFull, w1)) { if (w1) l_scan += chunk_mass(k1, xx, c0, a2); }
-        if (__any_sync(kFull, w2)) { if (w2) l_scan += chunk_mass(k2, xx, c0, a2); }
-        if (__any_sync(kFull, w3)) { if (w3) l_scan += chunk_mass(k3, xx, c0, a2); }
-        s0 = s0 && !w0; s1 = s1 && !w1; s2 = s2 && !w2; s3 = s3 && !w3;
-        if (!__any_sync(kFull, s0 || s1 || s2 || s3)) return;
-    }
-    push_chunk(k0, col0, s0, rg, lane, lanes_below);
-    push_chunk(k1, col0 + TC_CHUNK, s1, rg, lane, lanes_below);
-    push_chunk(k2, col0 + 2 * TC_CHUNK, s2, rg, lane, lanes_below);
-    push_chunk(k3, col0 + 3 * TC_CHUNK, s3, rg, lane, lanes_below);
+    tail += (unsigned)n;
+    if (n >= 8) { ring_publish(head_a + 8, tail, lane); pub = tail; }   // flood (start-up, dense softmax windows): do not sit on the entries
 }
 
 // priming pass: the scanner thread keeps the KP smallest CHUNK MINIMA it has seen in a sorted register list (a branch-free
@@ -363,14 +317,13 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     uint8_t* Ys = Xs + unit;                              // [NST][KB x 16 KB | 4 KB]: this CTA's 128 columns of every tile (half of N)
     uint8_t* q_mem = Ys + TC_NST * unit;                  // [TC_CONS_WARPS][Q_CAP][Q_ENTRY]
     // lists and row state are indexed by  li = column half * 128 + CTA-local row  (a row has one list per column half of the tile)
-    float* lkeys = reinterpret_cast<float*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][16] list keys (16-byte aligned rows)
-    int* lidx = reinterpret_cast<int*>(lkeys + TC_BM * LIST_STRIDE);                    // [256][16] list column indices
-    float2* thr2_s = reinterpret_cast<float2*>(lidx + TC_BM * LIST_STRIDE);             // [256] bounds read by the scanners: (max(list bound, softmax-window bound), list bound)
-    float* thr_list_s = reinterpret_cast<float*>(thr2_s + TC_BM);                       // [256] consumer-private row state from here on
+    float2* lists = reinterpret_cast<float2*>(q_mem + TC_CONS_WARPS * Q_CAP * Q_ENTRY);   // [256][LIST_STRIDE] (key, idx)
+    float* thr_hi_s = reinterpret_cast<float*>(lists + TC_BM * LIST_STRIDE);           // [256] bound read by the scanners
+    float* thr_list_s = thr_hi_s + TC_BM;                 // [256] consumer-private row state from here on
     float* thr_mass_s = thr_list_s + TC_BM;
-    float* kr_s = thr_mass_s + TC_BM;                     // smallest key seen (tightens the softmax window)
-    float* r_s = kr_s + TC_BM;                            // reference distance of the row's mass: starts at the priming pass' sampled minimum
-    float* l_s = r_s + TC_BM;                             // sum of exp2(-a2 (d - r)) over the non-candidate columns
+    float* kr_s = thr_mass_s + TC_BM;
+    float* r_s = kr_s + TC_BM;
+    float* l_s = r_s + TC_BM;
     float* xx_s = l_s + TC_BM;                            // [256] |x~|^2
     float* worst_s = xx_s + TC_BM;                        // [256] largest key of the row's list (slot number in its low bits)
     float* c0_s = worst_s + TC_BM;                        // [128] a2 * r0 per row (r0 = priming pass' sampled minimum): dense-window reference
@@ -405,10 +358,8 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
     // row state, lists and queue sequence words (all threads)
     for (int e = threadIdx.x; e < TC_CONS_WARPS * Q_CAP; e += TC_THREADS) *reinterpret_cast<unsigned*>(q_mem + e * Q_ENTRY + 72) = 0u;
-    for (int e = threadIdx.x; e < TC_BM * LIST_STRIDE; e += TC_THREADS) {    // empty slots: LIST_EMPTY with the slot number in the low bits
-        lkeys[e] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(e & 15));
-        lidx[e] = -1;
-    }
+    for (int e = threadIdx.x; e < TC_BM * LIST_STRIDE; e += TC_THREADS)      // empty slots: LIST_EMPTY with the slot number in the low bits
+        lists[e] = make_float2(__uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)((e % LIST_STRIDE) & 15)), __int_as_float(-1));
     for (int rl = threadIdx.x; rl < TC_BM; rl += TC_THREADS) {        // rl = li: both column halves start from the same state
         const int row = row0 + (rl & (TC_SUB - 1));
         float thl = -INFINITY, thm = -INFINITY, kr = INFINITY, r = INFINITY, xx = 0.f;   // padding rows never enqueue
@@ -429,7 +380,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = 0.f; xx_s[rl] = xx;
         if (rl < TC_SUB) c0_s[rl] = p.a2 * r;
         worst_s[rl] = __uint_as_float((__float_as_uint(LIST_EMPTY) & ~15u) | (unsigned)(K - 1));   // any empty slot: take the last
-        thr2_s[rl] = (p.debug & 1) ? make_float2(-INFINITY, -INFINITY) : make_float2(kSoft ? fmaxf(thl, thm) : thl, thl);
+        thr_hi_s[rl] = kSoft ? fmaxf(thl, thm) : thl;
     }
     if (warp == 1) {                        // TMEM of the pair: 512 columns per CTA (2 accumulator stages x 256), same warp in both CTAs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u) : "memory");
@@ -441,11 +392,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    // register redistribution: every role branch starts with the setmaxnreg of its warpgroup (whole warpgroups execute the
-    // same instruction; ptxas allocates the code of a branch against the budget its setmaxnreg sets)
-    if (warp < TC_LEAD_WARPS) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_LEAD));
-      if (warp == 0) {
+    if (warp == 0) {
         // =============================== TMA producer (both CTAs) ===============================
         if (lane == 0) {
             if (crank == 0) mbar_arrive_expect_tx(xfull, 2 * unit);                  // the pair's X rows: 2 x 128
@@ -462,7 +409,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 tma_load_3d_pair(&tmYe, full + s, dst + p.KB * TC_BLK_BYTES, 0, col0, b);
             }
         }
-      } else if (warp == 1) {
+    } else if (warp == 1) {
         // =============================== MMA issuer (leader CTA only) ===============================
         // One thread of the leader issues 9 tcgen05.mma.cta_group::2 per tile (M = 256 over the pair, N = 256, K = 16
         // each): every CTA feeds its own 128 rows of A and its own 128 columns of B from shared memory -- 8 KB per
@@ -503,73 +450,59 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 tc_commit_pair(tfull + acc);               // accumulators ready for the scanners of both CTAs
             }
         }
-      }   // warps 2, 3: nothing to do (they only hold the place of a whole warpgroup for setmaxnreg)
-    } else if (warp < TC_LEAD_WARPS + TC_SCAN_WARPS) {
+    } else if (warp < 2 + TC_SCAN_WARPS) {
         // =============================== scanners ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_SCAN));
-        const int ew = warp - TC_LEAD_WARPS;               // 0..15
-        const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's (TC_LEAD_WARPS % 4 == 0)
+        const int ew = warp - 2;                           // 0..15
+        const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31 are this warp's
         const int cgp = ew >> 2;                           // column group: columns cgp*64 .. +63 of each 256-column tile
         const int ch = cgp >> 1;                           // column half: the list / consumer this warp feeds
         const int cq = ch * 4 + quarter;                   // consumer / queue of this warp's (rows, column half)
-        const uint32_t thr2_a = smem_u32(thr2_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 8u;
+        const uint32_t thr_hi_a = smem_u32(thr_hi_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 4u;
+        const uint32_t q_a = smem_u32(q_mem) + (uint32_t)(cq * Q_CAP + (cgp & 1) * Q_SUB) * Q_ENTRY;   // this warp's own ring
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cq * sizeof(QCtl);
-        ScanRing rg;
-        rg.base = smem_u32(q_mem) + (uint32_t)(cq * Q_CAP + (cgp & 1) * Q_SUB) * Q_ENTRY;   // this warp's own ring
-        rg.head_a = ctl_a + (uint32_t)(cgp & 1) * 4u;
-        rg.tail = rg.head_seen = rg.pub = 0u;
-        const unsigned lanes_below = (1u << lane) - 1u;
+        const uint32_t head_a = ctl_a + (uint32_t)(cgp & 1) * 4u;
+        unsigned q_tail = 0, q_head_seen = 0, q_pub = 0;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgp * 64;
+        float priv = INFINITY;
+        DenseState ds;
+        ds.thl_a = smem_u32(thr_list_s) + (uint32_t)(ch * TC_SUB + quarter * 32 + lane) * 4u;
+        ds.xx = xx_s[quarter * 32 + lane]; ds.c0 = c0_s[quarter * 32 + lane]; ds.a2 = p.a2; ds.l = 0.f;
         float pl[KP];
 #pragma unroll
         for (int t = 0; t < KP; ++t) pl[t] = INFINITY;
-        int col0 = tile0 * TC_BN + cgp * 64;
-        const int col_step = p.tile_stride * TC_BN;
-        uint32_t aph = 0;
-        // dense-window mode: private softmax accumulator of this thread's (row, column group), reference r0 (priming pass)
-        float l_scan = 0.f;
-        const uint32_t sc_xx_a = smem_u32(xx_s + quarter * 32 + lane), sc_c0_a = smem_u32(c0_s + quarter * 32 + lane);
-
-        // one tile: wait for the accumulator stage, pull this thread's 64 columns into registers (four TMEM loads in flight,
-        // one wait), hand the stage back at once, then scan
-        auto tile = [&](const int acc) {
-            if (p.debug & 4) mbar_wait(tfull + acc, aph); else mbar_wait_backoff(tfull + acc, aph);
+#pragma unroll 1
+        for (int it = 0; it < ntiles; ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int col0 = (tile0 + it * p.tile_stride) * TC_BN + cgp * 64;
+            mbar_wait_backoff(tfull + acc, aph);
             tc_fence_after();
             const uint32_t taddr = t_lane + acc * TC_BN;
-            float k0[TC_CHUNK], k1[TC_CHUNK], k2[TC_CHUNK], k3[TC_CHUNK];
-            tc_ld16_issue(taddr, k0);
-            tc_ld16_issue(taddr + TC_CHUNK, k1);
-            tc_ld16_issue(taddr + 2 * TC_CHUNK, k2);
-            tc_ld16_issue(taddr + 3 * TC_CHUNK, k3);
-            float th = 0.f, thl = 0.f;                               // the row's published bounds: one read per tile
-            if (!kPrime) {
-                if (kDense) { const float2 t2 = lds_v2(thr2_a); th = t2.x; thl = t2.y; }
-                else th = lds_f32(thr2_a);
-            }
-            tc_ld16_wait(k0);
-            tc_ld16_after_wait(k1); tc_ld16_after_wait(k2); tc_ld16_after_wait(k3);
-            tc_fence_before();
+            // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is processed
+            float ka[TC_CHUNK], kb[TC_CHUNK];
+            tc_ld16_issue(taddr, ka);
+            tc_ld16_wait(ka);
+            tc_ld16_issue(taddr + TC_CHUNK, kb);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft, kDense>(ka, col0, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub, ds);
+            tc_ld16_wait(kb);
+            tc_ld16_issue(taddr + 2 * TC_CHUNK, ka);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft, kDense>(kb, col0 + TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub, ds);
+            tc_ld16_wait(ka);
+            tc_ld16_issue(taddr + 3 * TC_CHUNK, kb);
+            if (kPrime) prime_chunk(ka, pl); else scan_chunk<!kSoft, kDense>(ka, col0 + 2 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub, ds);
+            tc_ld16_wait(kb);
+            tc_fence_before();                               // all of this tile is in registers: hand the stage back
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty + acc);
-            if (kPrime) {
-                prime_chunk(k0, pl); prime_chunk(k1, pl); prime_chunk(k2, pl); prime_chunk(k3, pl);
-            } else if (p.debug & 2) {
-                if (k0[0] + k1[1] + k2[2] + k3[3] == 12345.678f) pl[0] = 0.f;      // keep the loads alive
-            } else {
-                scan_tile<kDense>(k0, k1, k2, k3, col0, th, thl, rg, lane, lanes_below, sc_xx_a, sc_c0_a, p.a2, l_scan);
-                if (rg.pub != rg.tail) { ring_publish(rg.head_a + 8, rg.tail, lane); rg.pub = rg.tail; }     // once per tile
-            }
-            col0 += col_step;
-        };
-#pragma unroll 1
-        for (int it = 0; it + 1 < ntiles; it += 2) { tile(0); tile(1); aph ^= 1u; }
-        if (ntiles & 1) tile(0);
+            if (kPrime) prime_chunk(kb, pl); else scan_chunk<!kSoft, kDense>(kb, col0 + 3 * TC_CHUNK, thr_hi_a, q_a, head_a, lane, lane, priv, it == 0, q_tail, q_head_seen, q_pub, ds);
+            if (q_pub != q_tail) { ring_publish(head_a + 8, q_tail, lane); q_pub = q_tail; }     // once per tile
+        }
         if (kDense)                                          // all MMAs have retired: the X block is free.  [4 column groups][128 rows]
-            reinterpret_cast<float*>(Xs)[cgp * TC_SUB + quarter * 32 + lane] = l_scan;
+            reinterpret_cast<float*>(Xs)[cgp * TC_SUB + quarter * 32 + lane] = ds.l;
         if (kPrime) {                                        // hand the sorted list of this column half to the row's consumer
-            float* L = lkeys + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
+            float2* L = lists + (ch * TC_SUB + quarter * 32 + lane) * LIST_STRIDE + (cgp & 1) * KP;
 #pragma unroll
-            for (int t = 0; t < KP; ++t) L[t] = pl[t];
+            for (int t = 0; t < KP; ++t) L[t] = make_float2(pl[t], 0.f);
         }
         __syncwarp();
         if (lane == 0) {
@@ -578,12 +511,11 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
     } else {
         // =============================== consumers ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CONS));
         // Row lists are UNSORTED K-slot sets in shared memory; every stored key carries its slot number in its 4 low
         // mantissa bits, so "the worst entry and where it sits" is one max-tree.  Entry keys get their column offset
         // packed the same way, so "the best not yet handled key and its column" is one min-tree.  (16 ulp of
         // perturbation, covered by the certificate's E2 term; exact distances are recomputed by finalize anyway.)
-        const int cw = warp - (TC_LEAD_WARPS + TC_SCAN_WARPS);   // consumer index: column half * 4 + quarter
+        const int cw = warp - (2 + TC_SCAN_WARPS);          // consumer index: column half * 4 + quarter
         const int rl0 = cw * 32;                             // first list index li served (column half * 128 + quarter * 32); `rl` below is li
         const uint32_t q_a = smem_u32(q_mem) + (uint32_t)cw * Q_CAP * Q_ENTRY;
         const uint32_t ctl_a = smem_u32(qctl) + (uint32_t)cw * sizeof(QCtl);
@@ -608,77 +540,30 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 __nanosleep(32);
                 continue;
             }
-            const bool active = (lane & 15) < (sub ? n1 : n0) && !(p.debug & 8);
+            const bool active = (lane & 15) < (sub ? n1 : n0);
             float k[TC_CHUNK];
             int rl = -1 - lane, cbase = 0;                            // inactive lanes: unique pseudo rows
-            float lim = -INFINITY;                                    // ONE snapshot of the row's list bound per entry
-            float mass = 0.f, thm_e = -INFINITY;
-            bool need_mass = false;
             if (active) {
                 const float4 k0 = lds_v4(ea), k1 = lds_v4(ea + 16), k2 = lds_v4(ea + 32), k3 = lds_v4(ea + 48);
                 k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
                 k[8] = k2.x; k[9] = k2.y; k[10] = k2.z; k[11] = k2.w; k[12] = k3.x; k[13] = k3.y; k[14] = k3.z; k[15] = k3.w;
                 const float2 rc = lds_v2(ea + 64);
                 rl = rl0 + __float_as_int(rc.x); cbase = __float_as_int(rc.y);
-                lim = fminf(thr_list_s[rl], worst_s[rl]);
-                if (kSoft) {
-                    // does the entry hold a NON-candidate key (>= lim) inside the softmax window?  (one min-tree; most entries
-                    // of a peaked softmax only carry their candidate)
-                    thm_e = thr_mass_s[rl];
-                    float nc[TC_CHUNK];
 #pragma unroll
-                    for (int t = 0; t < TC_CHUNK; ++t) nc[t] = k[t] >= lim ? k[t] : INFINITY;
-                    need_mass = min16(nc) < thm_e;
-                }
+                for (int t = 0; t < TC_CHUNK; ++t) k[t] = __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t);
             } else {
 #pragma unroll
                 for (int t = 0; t < TC_CHUNK; ++t) k[t] = INFINITY;
             }
-            if (kSoft && __any_sync(kFull, need_mass)) {
-                // terms of the keys that can never be candidates (>= lim), inside the softmax window, against the snapshot reference
-                if (need_mass) {
-                    const float xx = xx_s[rl], c0 = p.a2 * r_s[rl];
-#pragma unroll
-                    for (int t = 0; t < TC_CHUNK; ++t) {
-                        const float e = ex2_approx(fmaf(-p.a2, key_dist_fast(k[t], xx), c0));
-                        if (k[t] >= lim && k[t] < thm_e) mass += e;
-                    }
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < TC_CHUNK; ++t)                        // candidates keep their column offset in the 4 low bits
-                k[t] = k[t] < lim ? __uint_as_float((__float_as_uint(k[t]) & ~15u) | (unsigned)t) : INFINITY;
-            // the two smallest candidates of every entry, once per batch
-            const float m1 = min16(k);
-            float m2;
-            {
-                float cand[TC_CHUNK];
-#pragma unroll
-                for (int t = 0; t < TC_CHUNK; ++t) cand[t] = k[t] > m1 ? k[t] : INFINITY;
-                m2 = min16(cand);
-            }
+            // entries of the same row are processed one after the other, in queue order
             const unsigned peers = __match_any_sync(kFull, rl);
-            if (kSoft) {
-                // same-row lanes of the batch: the first one collects the others' sums and adds them to the row's accumulator
-                // (a row's state belongs to this warp alone: no atomic)
-                const int leader = __ffs(peers) - 1;
-                unsigned rest = peers & ~(1u << leader);
-                while (__any_sync(kFull, rest != 0u)) {
-                    const int src = rest ? __ffs(rest) - 1 : lane;
-                    const float other = __shfl_sync(kFull, mass, src);
-                    if (rest && lane == leader) mass += other;
-                    rest &= rest - 1u;
-                }
-                if (active && lane == leader && mass != 0.f) l_s[rl] += mass;
-            }
-            // entries with candidates: same-row entries one after the other, in queue order
-            bool todo = active && m1 < INFINITY;
-            unsigned done_mask = ~__ballot_sync(kFull, todo);
+            bool todo = active;
+            unsigned done_mask = ~__ballot_sync(kFull, active);       // inactive lanes count as done
             while (done_mask != kFull) {
                 const bool mine = todo && (__ffs(peers & ~done_mask) - 1 == lane);
                 // row state of the lanes whose turn it is
                 float xx = 0.f, thl = -INFINITY, thm = -INFINITY, kr = 0.f, r = 0.f, l = 0.f, worst = -INFINITY;
-                const int lb = (mine ? rl : 0) * LIST_STRIDE;
+                float2* L = lists + (mine ? rl : 0) * LIST_STRIDE;
                 if (mine) {
                     xx = xx_s[rl]; thl = thr_list_s[rl]; thm = thr_mass_s[rl]; kr = kr_s[rl]; r = r_s[rl]; l = l_s[rl];
                     worst = worst_s[rl];
@@ -687,53 +572,48 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 }
                 bool changed = false;
                 float prev = -INFINITY;                               // packed keys handled so far are <= prev
-                // warp-uniform loop: every trip handles the next-best candidate key of every lane that still has one.  The two
-                // smallest were found once per batch (m1, m2): the common single-candidate entry costs no second min-tree.
-                for (int trip = 0;; ++trip) {
+                // warp-uniform loop: every trip handles the next-best key of every lane that still has one below its bound
+                for (;;) {
                     float m;
-                    if (trip == 0) m = m1;
-                    else if (trip == 1) m = m2;
-                    else {
+                    if (prev == -INFINITY) {                          // first trip of a lane: plain minimum
+                        m = min16(k);
+                    } else {
                         float cand[TC_CHUNK];
 #pragma unroll
                         for (int t = 0; t < TC_CHUNK; ++t) cand[t] = k[t] > prev ? k[t] : INFINITY;
                         m = min16(cand);
                     }
-                    const bool go = mine && m < INFINITY;             // every key below the snapshot is settled here: list or mass
+                    if (kSoft && mine && m < kr) {                    // new row minimum: move the reference of the mass
+                        const float rn = key_dist_approx(m, xx);
+                        if (l != 0.f) l *= ex2_approx(-p.a2 * (r - rn));
+                        kr = m; r = rn;
+                        const float te = rn + p.cut_over_alpha;
+                        thm = 0.5f * (te * te - xx);
+                    }
+                    const float lim = fminf(thl, worst);
+                    const bool go = mine && m < (kSoft ? fmaxf(lim, thm) : lim);
                     if (!__any_sync(kFull, go)) break;
                     if (go) {
                         prev = m;
-                        if (kSoft && m < kr) {                        // new row minimum: move the reference of the row's mass
-                            const float rn = key_dist_fast(m, xx);
-                            if (l != 0.f) l *= ex2_approx(-p.a2 * (r - rn));
-                            kr = m; r = rn;
-                            const float te = rn + p.cut_over_alpha;
-                            thm = 0.5f * (te * te - xx);
-                        }
                         float out = m;
-                        if (m < fminf(thl, worst)) {                  // still a candidate: replace the worst entry, find the new worst
+                        if (m < lim) {                                // list candidate: replace the worst entry, find the new worst
                             out = worst;
                             const int ws = (int)(__float_as_uint(worst) & 15u);
-                            lkeys[lb + ws] = __uint_as_float((__float_as_uint(m) & ~15u) | (unsigned)ws);
-                            lidx[lb + ws] = cbase + (int)(__float_as_uint(m) & 15u);
-                            const float4* L4 = reinterpret_cast<const float4*>(lkeys + lb);
-                            const float4 a0 = L4[0], a1 = L4[1];
-                            float w = max3(max3(a0.x, a0.y, a0.z), max3(a0.w, a1.x, a1.y), fmaxf(a1.z, a1.w));
-                            if (K > 8) {
-                                const float4 a2 = L4[2], a3 = L4[3];
-                                w = max3(w, max3(max3(a2.x, a2.y, a2.z), max3(a2.w, a3.x, a3.y), fmaxf(a3.z, a3.w)), w);
-                            }
+                            L[ws] = make_float2(__uint_as_float((__float_as_uint(m) & ~15u) | (unsigned)ws),
+                                                __int_as_float(cbase + (int)(__float_as_uint(m) & 15u)));
+                            float w = -INFINITY;
+#pragma unroll
+                            for (int t = 0; t < K; ++t) w = fmaxf(w, L[t].x);
                             worst = w;
                             changed = true;
                         }
-                        // evicted / rejected key inside the softmax window (empty-slot markers are ~3e38: never)
-                        if (kSoft && out < fminf(thm, 1e37f)) l += ex2_approx(-p.a2 * (key_dist_fast(out, xx) - r));
+                        if (kSoft && out < thm) l += ex2_approx(-p.a2 * (key_dist_approx(out, xx) - r));
                     }
                 }
                 if (mine) {
                     thl = fminf(thl, worst);
                     thr_list_s[rl] = thl; thr_mass_s[rl] = thm; kr_s[rl] = kr; r_s[rl] = r; l_s[rl] = l; worst_s[rl] = worst;
-                    sts_v2(smem_u32(thr2_s + rl), kSoft ? fmaxf(thl, thm) : thl, thl);    // one 8-byte store: (bound, list bound) stay a consistent pair
+                    *reinterpret_cast<volatile float*>(thr_hi_s + rl) = kSoft ? fmaxf(thl, thm) : thl;
                     if (!kPrime && p.multi_split && changed && worst < LIST_EMPTY)
                         atomicMin(p.thr_global + (size_t)b * p.N + row0 + (rl & (TC_SUB - 1)), __float_as_uint(fmaxf(fmaf(2.f, worst, xx), 0.f)));
                     todo = false;
@@ -750,42 +630,42 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const int row = row0 + (rl & (TC_SUB - 1));
             if (row < p.N && (!kPrime || cw < 4)) {
                 const float xx = xx_s[rl];
-                const float* L = lkeys + rl * LIST_STRIDE;
+                const float2* L = lists + rl * LIST_STRIDE;
                 if (kPrime) {
                     // merge the four sorted lists of chunk minima (column groups; two sit in the other half's list slot):
                     // KP-th smallest of the union, and the minimum
-                    const float* L2 = L + TC_SUB * LIST_STRIDE;
+                    const float2* L2 = L + TC_SUB * LIST_STRIDE;
                     int i0 = 0, i1 = KP, i2 = 0, i3 = KP;
                     float w = INFINITY;
                     for (int t = 0; t < KP; ++t) {
-                        const float a0 = i0 < KP ? L[i0] : INFINITY, a1 = i1 < 2 * KP ? L[i1] : INFINITY;
-                        const float a2 = i2 < KP ? L2[i2] : INFINITY, a3 = i3 < 2 * KP ? L2[i3] : INFINITY;
+                        const float a0 = i0 < KP ? L[i0].x : INFINITY, a1 = i1 < 2 * KP ? L[i1].x : INFINITY;
+                        const float a2 = i2 < KP ? L2[i2].x : INFINITY, a3 = i3 < 2 * KP ? L2[i3].x : INFINITY;
                         const float m01 = fminf(a0, a1), m23 = fminf(a2, a3);
                         w = fminf(m01, m23);
                         if (m01 <= m23) { if (a0 <= a1) ++i0; else ++i1; } else { if (a2 <= a3) ++i2; else ++i3; }
                     }
-                    const float m = fminf(fminf(L[0], L[KP]), fminf(L2[0], L2[KP]));
-                    if (p.prime_thr && w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
+                    const float m = fminf(fminf(L[0].x, L[KP].x), fminf(L2[0].x, L2[KP].x));
+                    if (w < LIST_EMPTY) atomicMin(p.thr_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, w, xx), 0.f)));
                     if (m < LIST_EMPTY) atomicMin(p.rmin_global + (size_t)b * p.N + row, __float_as_uint(fmaxf(fmaf(2.f, m, xx), 0.f)));
                 } else {
                     const size_t g_row = (size_t)b * p.N + row;
                     const int part = split * 2 + (cw >> 2);                 // partial list index: (column split, column half)
                     const size_t base = (g_row * p.cb.P + part) * KC;
                     for (int t = 0; t < K; ++t) {
-                        const float ek = L[t];
-                        const bool has = ek < LIST_EMPTY;
-                        p.cb.key[base + t] = has ? fmaxf(fmaf(2.f, ek, xx), 0.f) : INFINITY;       // back to the true d^2 domain
-                        p.cb.idx[base + t] = has ? lidx[rl * LIST_STRIDE + t] : -1;
+                        const float2 e = L[t];
+                        const bool has = e.x < LIST_EMPTY;
+                        p.cb.key[base + t] = has ? fmaxf(fmaf(2.f, e.x, xx), 0.f) : INFINITY;      // back to the true d^2 domain
+                        p.cb.idx[base + t] = has ? __float_as_int(e.y) : -1;
                     }
                     const float thl = thr_list_s[rl];
                     float l_out = l_s[rl];
                     const float r_out = r_s[rl];
                     if (kDense) {
-                        // mass the scanners of this column half summed themselves (dense-window mode), reference r0 >= r_out
+                        // mass the scanners of this column half summed themselves, reference r0 >= r_out
                         const float* lsc = reinterpret_cast<const float*>(Xs) + (cw >> 2) * 2 * TC_SUB + (rl & (TC_SUB - 1));
                         const float ls = lsc[0] + lsc[TC_SUB];
                         if (ls != 0.f) {
-                            const float r0 = sqrtf(fmaxf(__uint_as_float(__ldcg(p.rmin_global + g_row)), 0.f));
+                            const float r0 = c0_s[rl & (TC_SUB - 1)] / p.a2;
                             l_out += ls * ex2_approx(-p.a2 * (r0 - r_out));
                         }
                     }
@@ -925,18 +805,17 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     p.xx = w.xx; p.cb = cb;
     p.thr_global = w.thr_g;
     p.rmin_global = w.rmin_g;
-    { const char* e = getenv("DVM_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     p.multi_split = 1;                               // the two column halves of a tile are separate lists that share thresholds
     p.tile_stride = 1;
     fill_u32_kernel<<<ceil_div(2 * B * N, 256), 256, 0, st>>>(w.thr_g, 0x7f800000u, 2 * B * N);    // +inf (memset cannot write it)
     DVM_LAUNCH_CHECK();
 
     const size_t unit = (size_t)p.KB * TC_BLK_BYTES + TC_EXT_BYTES;
-    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 9 * TC_BM * sizeof(float) + TC_SUB * sizeof(float)
+    const size_t smem = (1 + TC_NST) * unit + (size_t)TC_CONS_WARPS * Q_CAP * Q_ENTRY + (size_t)TC_BM * LIST_STRIDE * 8 + 8 * TC_BM * sizeof(float) + TC_SUB * sizeof(float)
                         + TC_CONS_WARPS * sizeof(QCtl) + 128;
-    // dense-window instance for small alpha (every chunk inside the softmax window): crossover measured between alpha = 10
-    // (141 -> 290 TFLOP/s at 50k) and alpha = 100 (810 -> 390 when forced)
-    const bool dense = soft && alpha < TC_DENSE_ALPHA;
+    // dense-window instance for small alpha (needs the priming pass' reference): crossover measured between alpha = 10
+    // (91 -> 300 TFLOP/s at 50k) and alpha = 100 (810 -> 390 when forced)
+    const bool dense = soft && alpha < TC_DENSE_ALPHA && p.tiles_total >= TC_PRIME_MIN_TILES;
     auto kern = !soft ? softmap_cand_tc_kernel<false, false> : dense ? softmap_cand_tc_kernel<true, false, true> : softmap_cand_tc_kernel<true, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
     static bool attr_done = false;
@@ -949,14 +828,9 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     }
     if (smem > 227 * 1024) { set_error("launch_cand_tc: C=%d needs %zu bytes of shared memory", C, smem); return DVM_ERR_UNSUPPORTED; }
     prof_begin(st);
-    {
-        // priming pass over every 10th tile (10 % of the sweep's MMA work): list threshold + the FIXED softmax reference of every
-        // row.  Small problems (< 16 tiles) sample every other tile and only take the reference from it.
+    if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 10th tile (10 % of the sweep's MMA work)
         TcParams pp = p;
-        const bool big = p.tiles_total >= TC_PRIME_MIN_TILES;
-        pp.tile_stride = big ? TC_PRIME_STRIDE : (p.tiles_total >= 2 ? 2 : 1);
-        pp.prime_thr = big ? 1 : 0;
-        pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
+        pp.tile_stride = TC_PRIME_STRIDE; pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
         dim3 gridp(2 * ceil_div(N, TC_BM), 1, B);                 // clusters of 2 CTAs along x
         kprime<<<gridp, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, pp);
         DVM_LAUNCH_CHECK();
