@@ -47,12 +47,12 @@ SIGNATURES = {
     "dvm_arap_workspace_bytes": (c_size_t, [c_int] * 2),
     "dvm_arap_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "dvm_arap_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 3),
-    "dvm_node_table": (c_int, [c_void_p] * 3 + [c_int] * 2 + [c_void_p] * 2),
-    "dvm_node_table_from_d9": (c_int, [c_void_p] * 2 + [c_int] * 2 + [c_void_p] * 4),
+    "dvm_node_table": (c_int, [c_void_p] * 4 + [c_int] * 2 + [c_void_p] * 2),
+    "dvm_node_table_from_d9": (c_int, [c_void_p] * 3 + [c_int] * 2 + [c_void_p] * 4),
     "dvm_skin_fwd_packed": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 2),
     "dvm_skin_bwd_csr": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p] * 3),
     "dvm_arap_packed_workspace_bytes": (c_size_t, [c_int] * 2),
-    "dvm_arap_fwd_packed": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
+    "dvm_arap_fwd_packed": (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "dvm_gather_conv_fwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 2),
     "dvm_gather_conv_bwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 4),
     "dvm_linear_act_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -19,17 +19,28 @@ __device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(s * a.x, s * 
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 
-__global__ void rot6d_fwd_kernel(const float* __restrict__ d6, int n, float* __restrict__ R) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float* p = d6 + (size_t)i * 6;
-    const V3 a1 = v3(p[0], p[1], p[2]), a2 = v3(p[3], p[4], p[5]);
-    const V3 b1 = (1.f / fmaxf(sqrtf(dot(a1, a1)), 1e-12f)) * a1;        // F.normalize, eps 1e-12
-    const V3 u = a2 - dot(b1, a2) * b1;
-    const V3 b2 = (1.f / fmaxf(sqrtf(dot(u, u)), 1e-12f)) * u;
-    const V3 b3 = cross(b1, b2);
-    float* o = R + (size_t)i * 9;
-    o[0] = b1.x; o[1] = b1.y; o[2] = b1.z; o[3] = b2.x; o[4] = b2.y; o[5] = b2.z; o[6] = b3.x; o[7] = b3.y; o[8] = b3.z;
+// one warp = 32 consecutive rotations: the 24-byte inputs and 36-byte outputs are moved as contiguous float runs (coalesced
+// 128-byte lines) through a per-warp shared-memory tile; strides 6 and 9 are conflict-free (6: 2-way at most).
+__global__ void __launch_bounds__(256) rot6d_fwd_kernel(const float* __restrict__ d6, int n, float* __restrict__ R) {
+    __shared__ float s_in[8][32 * 6], s_out[8][32 * 9];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = (blockIdx.x * 8 + w) * 32;
+    if (i0 >= n) return;
+    const int cnt = min(32, n - i0);
+    for (int e = lane; e < cnt * 6; e += 32) s_in[w][e] = __ldg(d6 + (size_t)i0 * 6 + e);
+    __syncwarp();
+    if (lane < cnt) {
+        const float* p = s_in[w] + lane * 6;
+        const V3 a1 = v3(p[0], p[1], p[2]), a2 = v3(p[3], p[4], p[5]);
+        const V3 b1 = (1.f / fmaxf(sqrtf(dot(a1, a1)), 1e-12f)) * a1;        // F.normalize, eps 1e-12
+        const V3 u = a2 - dot(b1, a2) * b1;
+        const V3 b2 = (1.f / fmaxf(sqrtf(dot(u, u)), 1e-12f)) * u;
+        const V3 b3 = cross(b1, b2);
+        float* o = s_out[w] + lane * 9;
+        o[0] = b1.x; o[1] = b1.y; o[2] = b1.z; o[3] = b2.x; o[4] = b2.y; o[5] = b2.z; o[6] = b3.x; o[7] = b3.y; o[8] = b3.z;
+    }
+    __syncwarp();
+    for (int e = lane; e < cnt * 9; e += 32) R[(size_t)i0 * 9 + e] = s_out[w][e];
 }
 
 __global__ void rot6d_bwd_kernel(const float* __restrict__ d6, const float* __restrict__ dR, int n, float* __restrict__ dd6) {
@@ -279,6 +290,7 @@ gather_conv_bwd_kernel(const float* __restrict__ feat, const int64_t* __restrict
 // ------------------------------------------------------------------------------------------------
 // sparse transfers  out[row,:] = sum_k w[row,k] Y[b, idx[row,k], :]
 // ------------------------------------------------------------------------------------------------
+// wide rows (D % 4 == 0, e.g. the 128 conv-reduced feature channels of models/model.py:471): one warp per output row, float4 lanes
 __global__ void __launch_bounds__(256)
 sparse_transfer_fwd_kernel(const int* __restrict__ idx, const float* __restrict__ w, const float* __restrict__ Y,
                            int rows, int N, int M, int K, int D, float* __restrict__ out) {
@@ -293,6 +305,19 @@ sparse_transfer_fwd_kernel(const int* __restrict__ idx, const float* __restrict_
         wk[k] = k < K ? __ldg(w + (size_t)row * K + k) : 0.f;
         jk[k] = k < K ? __ldg(idx + (size_t)row * K + k) : 0;
     }
+    if ((D & 3) == 0) {
+        for (int d = lane * 4; d < D; d += 128) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < DVM_KNN_MAX; ++k)
+                if (k < K && wk[k] != 0.f) {
+                    const float4 y = __ldg(reinterpret_cast<const float4*>(Yb + (size_t)jk[k] * D + d));
+                    acc.x = fmaf(wk[k], y.x, acc.x); acc.y = fmaf(wk[k], y.y, acc.y); acc.z = fmaf(wk[k], y.z, acc.z); acc.w = fmaf(wk[k], y.w, acc.w);
+                }
+            *reinterpret_cast<float4*>(out + (size_t)row * D + d) = acc;
+        }
+        return;
+    }
     for (int d = lane; d < D; d += 32) {
         float acc = 0.f;
 #pragma unroll
@@ -300,6 +325,30 @@ sparse_transfer_fwd_kernel(const int* __restrict__ idx, const float* __restrict_
             if (k < K && wk[k] != 0.f) acc = fmaf(wk[k], __ldg(Yb + (size_t)jk[k] * D + d), acc);
         out[(size_t)row * D + d] = acc;
     }
+}
+
+// narrow rows (D <= 4: Pi @ verts, models/loss.py:1408-1409): one THREAD per output row (a warp per row leaves 29 lanes idle)
+template <int kD>
+__global__ void __launch_bounds__(256)
+sparse_transfer_fwd_narrow_kernel(const int* __restrict__ idx, const float* __restrict__ w, const float* __restrict__ Y,
+                                  int rows, int N, int M, int K, float* __restrict__ out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int b = row / N;
+    const float* Yb = Y + (size_t)b * M * kD;
+    float acc[kD];
+#pragma unroll
+    for (int d = 0; d < kD; ++d) acc[d] = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float wk = __ldg(w + (size_t)row * K + k);
+        const int j = __ldg(idx + (size_t)row * K + k);
+        if (wk != 0.f) {
+#pragma unroll
+            for (int d = 0; d < kD; ++d) acc[d] = fmaf(wk, __ldg(Yb + (size_t)j * kD + d), acc[d]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < kD; ++d) out[(size_t)row * kD + d] = acc[d];
 }
 
 __global__ void __launch_bounds__(256)
@@ -332,7 +381,7 @@ using namespace dvm;
 
 extern "C" int dvm_rot6d_fwd(const float* d6, int n, float* R, void* stream) {
     DVM_CHECK_ARG(d6 && R && n > 0, "dvm_rot6d_fwd: bad arguments");
-    rot6d_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d6, n, R);
+    rot6d_fwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d6, n, R);       // 8 warps x 32 rotations per block
     DVM_LAUNCH_CHECK();
     return 0;
 }
@@ -413,7 +462,11 @@ extern "C" int dvm_sparse_transfer_fwd(const int32_t* idx, const float* w, const
     DVM_CHECK_ARG(idx && w && Y && out, "dvm_sparse_transfer_fwd: null pointer");
     DVM_CHECK_ARG(B > 0 && N > 0 && M > 0 && D > 0 && K > 0 && K <= DVM_KNN_MAX, "dvm_sparse_transfer_fwd: bad sizes");
     const int rows = B * N;
-    sparse_transfer_fwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(idx, w, Y, rows, N, M, K, D, out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D == 3)      sparse_transfer_fwd_narrow_kernel<3><<<ceil_div(rows, 256), 256, 0, st>>>(idx, w, Y, rows, N, M, K, out);
+    else if (D == 1) sparse_transfer_fwd_narrow_kernel<1><<<ceil_div(rows, 256), 256, 0, st>>>(idx, w, Y, rows, N, M, K, out);
+    else if (D == 2) sparse_transfer_fwd_narrow_kernel<2><<<ceil_div(rows, 256), 256, 0, st>>>(idx, w, Y, rows, N, M, K, out);
+    else             sparse_transfer_fwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(idx, w, Y, rows, N, M, K, D, out);
     DVM_LAUNCH_CHECK();
     return 0;
 }

@@ -4,12 +4,15 @@
 //
 //   node record  float4[4] = 64 B, 64-byte aligned:  q0 = R0..R3 | q1 = R4..R7 | q2 = R8, t0, t1, t2 | q3 = g0, g1, g2, 0
 //                (t and g share one 32-byte sector: ARAP without the smoothness term reads ONE sector per ring neighbour);
-//   vorder  int32[B][N]     vertices in Morton order of their coordinates: consecutive threads work on spatial neighbours,
-//                           which share their influencing nodes, so node records are L1/L2 hits (each node influences ~6 vertices);
-//   s_infl  int32[B][3][N], s_w f32[B][3][N]   influence lists of vertex vorder[i], slot-major: every load of a warp is one
-//                           contiguous 128-byte line;
-//   norder  int32[B][K], s_ring int32[B][9][K]  the same for the node ring (ARAP);
-//   csr_ptr int32[B][K+1], csr_vert int32[B][3N], csr_w f32[B][3N]   vertex lists per node for the skinning backward: one
+//   NODES ARE RENUMBERED in Morton order of their positions (node_perm[new] = old; the Deformer is asked for its rows in that
+//   order, so the per-step node table comes out Morton-ordered for free): spatial neighbours are memory neighbours, the
+//   records a warp of neighbouring vertices gathers share sectors and stay in L1;
+//   vorder  int32[B][N]     vertices in Morton order of their coordinates, s_xyz f32[B][N][3] the same vertices' coordinates
+//                           (static per shape: streamed, not gathered); the warped points are scattered back through vorder;
+//   s_infl  int32[B][3][N], s_w f32[B][3][N]   influence lists (new node numbers) of vertex vorder[i], slot-major: every load
+//                           of a warp is one contiguous 128-byte line;
+//   s_ring int32[B][9][K]   ring of (new) node i, new node numbers, slot-major;
+//   csr_ptr int32[B][K+1], csr_vert int32[B][3N], csr_w f32[B][3N]   vertex lists per (new) node for the skinning backward: one
 //                           thread owns a node and sums its vertices in ascending vertex order -- no atomics, deterministic.
 //
 // DRAM bytes per vertex (skinning): vorder 4 + s_infl 12 + s_w 12 + xyz 12 + out 12 = 52, + node records 64 B / node = 32 B /
@@ -38,9 +41,12 @@ __device__ __forceinline__ P3 ldp3(const float* p) { return p3(__ldg(p), __ldg(p
 // ------------------------------------------------------------------------------------------------
 constexpr int NT_WARPS = 8;
 
+// perm (may be null): input row of node i is perm[i] within its cloud of K nodes (inputs in the caller's node order, table in
+// Morton order); with a permutation the 48-byte inputs are gathered per node instead of streamed.
 template <bool kFromD9>
 __global__ void __launch_bounds__(NT_WARPS * 32)
 node_table_kernel(const float* __restrict__ Rin, const float* __restrict__ tin, const float* __restrict__ g, int n,
+                  const int* __restrict__ perm, int K,
                   float4* __restrict__ table, float* __restrict__ R_out, float* __restrict__ t_out) {
     __shared__ float s_in[NT_WARPS][32 * 9 + 32 * 3 + 32 * 3];
     __shared__ __align__(16) float s_rec[NT_WARPS][32 * 16];
@@ -50,11 +56,22 @@ node_table_kernel(const float* __restrict__ Rin, const float* __restrict__ tin, 
     const int cnt = min(32, n - node0);
     float* in = s_in[w];
     {
-        const float* src = Rin + (size_t)node0 * 9;                       // R rows or d9 rows: 9 floats per node
-        for (int e = lane; e < cnt * 9; e += 32) in[e] = __ldg(src + e);
-        if (!kFromD9) {
-            const float* ts = tin + (size_t)node0 * 3;
-            for (int e = lane; e < cnt * 3; e += 32) in[288 + e] = __ldg(ts + e);
+        if (perm == nullptr) {
+            const float* src = Rin + (size_t)node0 * 9;                   // R rows or d9 rows: 9 floats per node
+            for (int e = lane; e < cnt * 9; e += 32) in[e] = __ldg(src + e);
+            if (!kFromD9) {
+                const float* ts = tin + (size_t)node0 * 3;
+                for (int e = lane; e < cnt * 3; e += 32) in[288 + e] = __ldg(ts + e);
+            }
+        } else if (lane < cnt) {
+            const int i = node0 + lane;
+            const size_t srow = (size_t)(i / K) * K + __ldg(perm + i);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) in[lane * 9 + c] = __ldg(Rin + srow * 9 + c);
+            if (!kFromD9) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) in[288 + lane * 3 + c] = __ldg(tin + srow * 3 + c);
+            }
         }
         const float* gs = g + (size_t)node0 * 3;
         for (int e = lane; e < cnt * 3; e += 32) in[384 + e] = __ldg(gs + e);
@@ -111,13 +128,13 @@ node_table_kernel(const float* __restrict__ Rin, const float* __restrict__ tin, 
 // skinning forward on the packed layout: thread = one vertex in Morton order
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-skin_fwd_packed_kernel(const float* __restrict__ xyz, const int* __restrict__ vorder, const int* __restrict__ s_infl,
+skin_fwd_packed_kernel(const float* __restrict__ s_xyz, const int* __restrict__ vorder, const int* __restrict__ s_infl,
                        const float* __restrict__ s_w, const float4* __restrict__ table, int N, int K, float* __restrict__ out) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int vid = __ldg(vorder + (size_t)b * N + i);
-    const P3 v = ldp3(xyz + ((size_t)b * N + vid) * 3);
+    const P3 v = ldp3(s_xyz + ((size_t)b * N + i) * 3);
     const float4* tb = table + (size_t)b * K * 4;
     int nk[3]; float wk[3];
 #pragma unroll
@@ -176,14 +193,14 @@ skin_bwd_csr_kernel(const float* __restrict__ xyz, const float* __restrict__ nod
 }
 
 // ------------------------------------------------------------------------------------------------
-// ARAP (+ optional rotation smoothness) on the packed layout: thread = one node in Morton order of the node positions;
+// ARAP (+ optional rotation smoothness) on the packed layout: thread = one node (nodes are numbered in Morton order);
 // per-block partial sums, fixed-order final sum (deterministic)
 // ------------------------------------------------------------------------------------------------
 constexpr int AP_THREADS = 256;
 
 template <bool kSr>
 __global__ void __launch_bounds__(AP_THREADS)
-arap_fwd_packed_kernel(const int* __restrict__ norder, const int* __restrict__ s_ring, const float4* __restrict__ table,
+arap_fwd_packed_kernel(const int* __restrict__ s_ring, const float4* __restrict__ table,
                        int K, int ring_k, float* __restrict__ part /* [B][gridDim.x][2] */) {
     __shared__ float s[2][AP_THREADS / 32];
     const int b = blockIdx.y;
@@ -191,8 +208,7 @@ arap_fwd_packed_kernel(const int* __restrict__ norder, const int* __restrict__ s
     float a_sum = 0.f, r_sum = 0.f;
     if (i < K) {
         const float4* tb = table + (size_t)b * K * 4;
-        const int nid = __ldg(norder + (size_t)b * K + i);
-        const float4* rec = tb + (size_t)nid * 4;
+        const float4* rec = tb + (size_t)i * 4;
         const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
         const P3 gi = p3(q3.x, q3.y, q3.z), ti = p3(q2.y, q2.z, q2.w);
         for (int q = 0; q < ring_k; ++q) {
@@ -242,18 +258,18 @@ __global__ void arap_final_packed_kernel(const float* __restrict__ part, int nbl
 
 using namespace dvm;
 
-extern "C" int dvm_node_table(const float* R, const float* t, const float* nodes_xyz, int B, int K, float* table, void* stream) {
+extern "C" int dvm_node_table(const float* R, const float* t, const float* nodes_xyz, const int32_t* node_perm, int B, int K, float* table, void* stream) {
     DVM_CHECK_ARG(R && t && nodes_xyz && table, "dvm_node_table: null pointer");
     DVM_CHECK_ARG(B > 0 && K > 0 && (long long)B * K < 0x7fffffffLL, "dvm_node_table: bad sizes");
     DVM_CHECK_ARG(((uintptr_t)table & 63) == 0, "dvm_node_table: table must be 64-byte aligned");
     const int n = B * K;
     node_table_kernel<false><<<ceil_div(n, NT_WARPS * 32), NT_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        R, t, nodes_xyz, n, reinterpret_cast<float4*>(table), nullptr, nullptr);
+        R, t, nodes_xyz, n, node_perm, K, reinterpret_cast<float4*>(table), nullptr, nullptr);
     DVM_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int dvm_node_table_from_d9(const float* d9, const float* nodes_xyz, int B, int K, float* table,
+extern "C" int dvm_node_table_from_d9(const float* d9, const float* nodes_xyz, const int32_t* node_perm, int B, int K, float* table,
                                       float* R_out, float* t_out, void* stream) {
     DVM_CHECK_ARG(d9 && nodes_xyz && table, "dvm_node_table_from_d9: null pointer");
     DVM_CHECK_ARG((R_out == nullptr) == (t_out == nullptr), "dvm_node_table_from_d9: R_out and t_out come together");
@@ -261,17 +277,17 @@ extern "C" int dvm_node_table_from_d9(const float* d9, const float* nodes_xyz, i
     DVM_CHECK_ARG(((uintptr_t)table & 63) == 0, "dvm_node_table_from_d9: table must be 64-byte aligned");
     const int n = B * K;
     node_table_kernel<true><<<ceil_div(n, NT_WARPS * 32), NT_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        d9, nullptr, nodes_xyz, n, reinterpret_cast<float4*>(table), R_out, t_out);
+        d9, nullptr, nodes_xyz, n, node_perm, K, reinterpret_cast<float4*>(table), R_out, t_out);
     DVM_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int dvm_skin_fwd_packed(const float* xyz, const int32_t* vorder, const int32_t* s_infl, const float* s_w,
+extern "C" int dvm_skin_fwd_packed(const float* s_xyz, const int32_t* vorder, const int32_t* s_infl, const float* s_w,
                                    const float* table, int B, int N, int K, float* out, void* stream) {
-    DVM_CHECK_ARG(xyz && vorder && s_infl && s_w && table && out, "dvm_skin_fwd_packed: null pointer");
+    DVM_CHECK_ARG(s_xyz && vorder && s_infl && s_w && table && out, "dvm_skin_fwd_packed: null pointer");
     DVM_CHECK_ARG(B > 0 && N > 0 && K > 0 && B <= 65535, "dvm_skin_fwd_packed: bad sizes");
     skin_fwd_packed_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, (cudaStream_t)stream>>>(
-        xyz, vorder, s_infl, s_w, reinterpret_cast<const float4*>(table), N, K, out);
+        s_xyz, vorder, s_infl, s_w, reinterpret_cast<const float4*>(table), N, K, out);
     DVM_LAUNCH_CHECK();
     return 0;
 }
@@ -290,16 +306,16 @@ extern "C" size_t dvm_arap_packed_workspace_bytes(int B, int K) {
     return align_up((size_t)B * ceil_div(K, AP_THREADS) * 2 * sizeof(float), 256);
 }
 
-extern "C" int dvm_arap_fwd_packed(const int32_t* norder, const int32_t* s_ring, const float* table, int B, int K, int ring_k,
+extern "C" int dvm_arap_fwd_packed(const int32_t* s_ring, const float* table, int B, int K, int ring_k,
                                    float* arap, float* sr, void* ws, size_t ws_bytes, void* stream) {
-    DVM_CHECK_ARG(norder && s_ring && table && arap, "dvm_arap_fwd_packed: null pointer");
+    DVM_CHECK_ARG(s_ring && table && arap, "dvm_arap_fwd_packed: null pointer");
     DVM_CHECK_ARG(B > 0 && K > 0 && ring_k > 0 && B <= 65535, "dvm_arap_fwd_packed: bad sizes");
     if (!ws || ws_bytes < dvm_arap_packed_workspace_bytes(B, K)) { set_error("dvm_arap_fwd_packed: workspace too small"); return DVM_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = ceil_div(K, AP_THREADS);
     const float4* tb = reinterpret_cast<const float4*>(table);
-    if (sr) arap_fwd_packed_kernel<true><<<dim3(nblk, B), AP_THREADS, 0, st>>>(norder, s_ring, tb, K, ring_k, (float*)ws);
-    else    arap_fwd_packed_kernel<false><<<dim3(nblk, B), AP_THREADS, 0, st>>>(norder, s_ring, tb, K, ring_k, (float*)ws);
+    if (sr) arap_fwd_packed_kernel<true><<<dim3(nblk, B), AP_THREADS, 0, st>>>(s_ring, tb, K, ring_k, (float*)ws);
+    else    arap_fwd_packed_kernel<false><<<dim3(nblk, B), AP_THREADS, 0, st>>>(s_ring, tb, K, ring_k, (float*)ws);
     DVM_LAUNCH_CHECK();
     arap_final_packed_kernel<<<B, 32, 0, st>>>((const float*)ws, nblk, K, ring_k, arap, sr);
     DVM_LAUNCH_CHECK();

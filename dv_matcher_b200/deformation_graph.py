@@ -22,19 +22,28 @@ from .geometry import rotation_6d_to_matrix  # noqa: F401  (re-exported for call
 
 @dataclass
 class GraphPack:
-    """HBM-shaped copy of the graph tensors the per-step kernels stream (static per shape; see csrc/deform_packed.cu)."""
-    nodes_xyz: torch.Tensor     # f32   [B,K,3]   g = xyz[nodes_idx]
+    """HBM-shaped copy of the graph tensors the per-step kernels stream (static per shape; see csrc/deform_packed.cu).
+    Nodes are RENUMBERED in Morton order of their positions: node_perm[new] = old (the reference's FPS order)."""
+    node_perm: torch.Tensor     # int32 [B,K]     new -> old node number
+    nodes_idx_m: torch.Tensor   # int64 [B,K]     vertex index of every node, NEW order (what the Deformer is asked for: `fps1`)
+    nodes_xyz: torch.Tensor     # f32   [B,K,3]   node positions, new order
     vorder: torch.Tensor        # int32 [B,N]     vertices in Morton order
-    s_infl: torch.Tensor        # int32 [B,3,N]   influence lists of vertex vorder[i], slot-major
+    s_xyz: torch.Tensor         # f32   [B,N,3]   coordinates of vertex vorder[i]
+    s_infl: torch.Tensor        # int32 [B,3,N]   influence lists (new node numbers) of vertex vorder[i], slot-major
     s_w: torch.Tensor           # f32   [B,3,N]
-    norder: torch.Tensor        # int32 [B,K]     nodes in Morton order
-    s_ring: torch.Tensor        # int32 [B,9,K]   ring of node norder[i], slot-major
-    csr_ptr: torch.Tensor       # int32 [B,K+1]   vertices influenced by each node ...
+    s_ring: torch.Tensor        # int32 [B,9,K]   ring of new node i (new numbers), slot-major
+    csr_ptr: torch.Tensor       # int32 [B,K+1]   vertices influenced by each new node ...
     csr_vert: torch.Tensor      # int32 [B,3N]    ... ascending vertex id
     csr_w: torch.Tensor         # f32   [B,3N]
 
     def tensors(self):
-        return (self.nodes_xyz, self.vorder, self.s_infl, self.s_w, self.norder, self.s_ring, self.csr_ptr, self.csr_vert, self.csr_w)
+        return (self.node_perm, self.nodes_idx_m, self.nodes_xyz, self.vorder, self.s_xyz, self.s_infl, self.s_w, self.s_ring,
+                self.csr_ptr, self.csr_vert, self.csr_w)
+
+    def to_old_order(self, per_node):
+        """[B,K,...] tensor with rows in the packed (new) node order -> the reference's node order."""
+        idx = self.node_perm.long().reshape(*self.node_perm.shape, *([1] * (per_node.dim() - 2))).expand_as(per_node)
+        return torch.empty_like(per_node).scatter_(1, idx, per_node)
 
 
 @dataclass
@@ -100,23 +109,29 @@ def pack_graph(verts, nodes_idx, influence, weights, ring):
     """Streaming layout of a graph (once per shape; plain torch ops -- this is graph construction, not the per-step path)."""
     B, N, _ = verts.shape
     K = nodes_idx.shape[1]
-    nodes_xyz = torch.gather(verts, 1, nodes_idx[..., None].expand(B, K, 3)).contiguous()
+    g_old = torch.gather(verts, 1, nodes_idx[..., None].expand(B, K, 3))
+    node_perm = _morton_order(g_old)                                      # new -> old
+    no = node_perm.long()
+    inv = torch.empty_like(no).scatter_(1, no, torch.arange(K, device=verts.device).expand(B, K))     # old -> new
+    nodes_idx_m = torch.gather(nodes_idx, 1, no).contiguous()
+    nodes_xyz = torch.gather(g_old, 1, no[..., None].expand(B, K, 3)).contiguous()
+    infl_new = torch.gather(inv, 1, influence.reshape(B, 3 * N)).reshape(B, N, 3)                     # new node numbers
     vorder = _morton_order(verts)
     vo = vorder.long()
-    s_infl = torch.gather(influence, 1, vo[..., None].expand(B, N, 3)).transpose(1, 2).to(torch.int32).contiguous()
+    s_xyz = torch.gather(verts, 1, vo[..., None].expand(B, N, 3)).contiguous()
+    s_infl = torch.gather(infl_new, 1, vo[..., None].expand(B, N, 3)).transpose(1, 2).to(torch.int32).contiguous()
     s_w = torch.gather(weights, 1, vo[..., None].expand(B, N, 3)).transpose(1, 2).contiguous()
-    norder = _morton_order(nodes_xyz)
-    no = norder.long()
     rk = ring.shape[2]
-    s_ring = torch.gather(ring, 1, no[..., None].expand(B, K, rk)).transpose(1, 2).to(torch.int32).contiguous()
-    flat = influence.reshape(B, 3 * N)
-    order = torch.argsort(flat, dim=1, stable=True)                       # entries (v, k) sorted by node, ascending v within a node
+    ring_rows = torch.gather(ring, 1, no[..., None].expand(B, K, rk))                                  # rings of the nodes in new order ...
+    s_ring = torch.gather(inv, 1, ring_rows.reshape(B, K * rk)).reshape(B, K, rk).transpose(1, 2).to(torch.int32).contiguous()   # ... new numbers
+    flat = infl_new.reshape(B, 3 * N)
+    order = torch.argsort(flat, dim=1, stable=True)                       # entries (v, k) sorted by new node, ascending v within a node
     csr_vert = (order // 3).to(torch.int32).contiguous()
     csr_w = torch.gather(weights.reshape(B, 3 * N), 1, order).contiguous()
     counts = torch.zeros(B, K, dtype=torch.int64, device=verts.device).scatter_add_(1, flat, torch.ones_like(flat))
     csr_ptr = torch.zeros(B, K + 1, dtype=torch.int32, device=verts.device)
     csr_ptr[:, 1:] = counts.cumsum(1).to(torch.int32)
-    return GraphPack(nodes_xyz, vorder, s_infl, s_w, norder, s_ring, csr_ptr, csr_vert, csr_w)
+    return GraphPack(node_perm, nodes_idx_m, nodes_xyz, vorder, s_xyz, s_infl, s_w, s_ring, csr_ptr, csr_vert, csr_w)
 
 
 def build_graphs(verts, start=None):
@@ -136,7 +151,7 @@ class _Deform(torch.autograd.Function):
     @staticmethod
     def forward(ctx, verts, R, t, graph, want_sr):
         verts, R, t = verts.float().contiguous(), R.float().contiguous(), t.float().contiguous()
-        table = ops.node_table(R, t, graph.pack.nodes_xyz)
+        table = ops.node_table(R, t, graph.pack.nodes_xyz, node_perm=graph.pack.node_perm)      # R, t arrive in the reference's node order
         warped = ops.skin_fwd_packed(verts, graph.pack, table)
         arap, sr = ops.arap_fwd_packed(graph.pack, table, want_sr)
         ctx.save_for_backward(verts, R, t)
@@ -151,6 +166,7 @@ class _Deform(torch.autograd.Function):
         verts, R, t = ctx.saved_tensors
         g = ctx.graph
         dR, dt = ops.skin_bwd_csr(verts, g.pack, d_warped.contiguous())
+        dR, dt = g.pack.to_old_order(dR), g.pack.to_old_order(dt)                                     # packed (Morton) -> reference node order
         ops.arap_bwd(verts, g.nodes_idx, g.ring, R, t, d_arap.contiguous(), dR, dt)
         return None, dR, dt, None, None
 
@@ -163,12 +179,14 @@ def deform_batched(verts, graph, R, t, want_sr=True):
     return _Deform.apply(verts, R, t, graph, want_sr)
 
 
-def deform_from_d9(verts, graph, d9, want_sr=False):
+def deform_from_d9(verts, graph, d9, want_sr=False, packed_order=True):
     """Inference form fused with models/loss.py:1257-1264: d9 [B,K,9] is the Deformer output (t, 6D residual); the
-    identity offset, 6D -> R and the node-record packing are one kernel.  Returns (warped, arap, sr or None)."""
+    identity offset, 6D -> R and the node-record packing are one kernel.  packed_order: the rows of d9 follow
+    graph.pack.nodes_idx_m (the Deformer was called with fps1 = pack.nodes_idx_m), else graph.nodes_idx.
+    Returns (warped, arap, sr or None)."""
     if graph.pack is None:
         graph.pack = pack_graph(verts.float().contiguous(), graph.nodes_idx, graph.influence, graph.weights, graph.ring)
-    table = ops.node_table_from_d9(d9, graph.pack.nodes_xyz)
+    table = ops.node_table_from_d9(d9, graph.pack.nodes_xyz, node_perm=None if packed_order else graph.pack.node_perm)
     warped = ops.skin_fwd_packed(verts, graph.pack, table)
     arap, sr = ops.arap_fwd_packed(graph.pack, table, want_sr)
     return warped, arap, sr

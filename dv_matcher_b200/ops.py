@@ -249,18 +249,19 @@ def arap_bwd(xyz, nodes_idx, ring, R, t, g_arap, dR, dt):
     return dR, dt
 
 
-def node_table(R, t, nodes_xyz):
-    """Pack (R [B,K,3,3], t [B,K,3], g [B,K,3]) into 64-byte node records [B,K,16] (dvm_node_table)."""
+def node_table(R, t, nodes_xyz, node_perm=None):
+    """Pack (R [B,K,3,3], t [B,K,3], g [B,K,3]) into 64-byte node records [B,K,16] (dvm_node_table).  With node_perm
+    (int32 [B,K], new -> old) R and t are in the reference's node order and the table comes out in the packed (Morton) order."""
     lib = _lib.load()
     R, t, nodes_xyz = f32c(R), f32c(t), f32c(nodes_xyz)
     require_device(R)
     B, K = nodes_xyz.shape[0], nodes_xyz.shape[1]
     table = torch.empty(B, K, 16, dtype=torch.float32, device=R.device)
-    check(lib.dvm_node_table(ptr(R), ptr(t), ptr(nodes_xyz), B, K, ptr(table), stream_ptr()), "dvm_node_table")
+    check(lib.dvm_node_table(ptr(R), ptr(t), ptr(nodes_xyz), ptr(node_perm, torch.int32), B, K, ptr(table), stream_ptr()), "dvm_node_table")
     return table
 
 
-def node_table_from_d9(d9, nodes_xyz, want_rt=False):
+def node_table_from_d9(d9, nodes_xyz, want_rt=False, node_perm=None):
     """Deformer output d9 [B,K,9] -> node records (identity offset + 6D -> R fused; dvm_node_table_from_d9).
     Returns table or (table, R [B,K,3,3], t [B,K,3])."""
     lib = _lib.load()
@@ -270,7 +271,8 @@ def node_table_from_d9(d9, nodes_xyz, want_rt=False):
     table = torch.empty(B, K, 16, dtype=torch.float32, device=d9.device)
     R = torch.empty(B, K, 3, 3, dtype=torch.float32, device=d9.device) if want_rt else None
     t = torch.empty(B, K, 3, dtype=torch.float32, device=d9.device) if want_rt else None
-    check(lib.dvm_node_table_from_d9(ptr(d9), ptr(nodes_xyz), B, K, ptr(table), ptr(R), ptr(t), stream_ptr()), "dvm_node_table_from_d9")
+    check(lib.dvm_node_table_from_d9(ptr(d9), ptr(nodes_xyz), ptr(node_perm, torch.int32), B, K, ptr(table), ptr(R), ptr(t), stream_ptr()),
+          "dvm_node_table_from_d9")
     return (table, R, t) if want_rt else table
 
 
@@ -282,7 +284,7 @@ def skin_fwd_packed(xyz, pack, table):
     B, N, _ = xyz.shape
     K = table.shape[1]
     out = torch.empty_like(xyz)
-    check(lib.dvm_skin_fwd_packed(ptr(xyz), ptr(pack.vorder, torch.int32), ptr(pack.s_infl, torch.int32), ptr(pack.s_w, torch.float32),
+    check(lib.dvm_skin_fwd_packed(ptr(pack.s_xyz, torch.float32), ptr(pack.vorder, torch.int32), ptr(pack.s_infl, torch.int32), ptr(pack.s_w, torch.float32),
                                   ptr(table, torch.float32), B, N, K, ptr(out), stream_ptr()), "dvm_skin_fwd_packed")
     return out
 
@@ -307,7 +309,7 @@ def arap_fwd_packed(pack, table, want_sr=True):
     arap = torch.empty(B, dtype=torch.float32, device=table.device)
     sr = torch.empty(B, dtype=torch.float32, device=table.device) if want_sr else None
     ws = _lib.workspace.get(lib.dvm_arap_packed_workspace_bytes(B, K), table.device, "arap")
-    check(lib.dvm_arap_fwd_packed(ptr(pack.norder, torch.int32), ptr(pack.s_ring, torch.int32), ptr(table, torch.float32), B, K, rk,
+    check(lib.dvm_arap_fwd_packed(ptr(pack.s_ring, torch.int32), ptr(table, torch.float32), B, K, rk,
                                   ptr(arap), ptr(sr), ptr(ws), ws.numel(), stream_ptr()), "dvm_arap_fwd_packed")
     return arap, sr
 

@@ -51,8 +51,8 @@ def match_deform_stacked(fsrc, ftgt, src, tgt, graphs, deformer, alpha=100.0, k_
     sm, vt = maps.soft_map(fsrc, ftgt, alpha, v=tgt, prec=prec)            # [2B,...]: rows 0..B-1 = 1->2, B..2B-1 = 2->1
     idx_self = ops.knn3(src, src, k_deform)                                # idx11 | idx22  (models/loss.py:1229-1230)
     idx_tgt = torch.cat([idx_self[B:], idx_self[:B]])
-    fps = graphs.nodes_idx
-    deformations = deformer.forward_fused(fsrc, ftgt, idx_self, idx_tgt, src, vt, sm, fps)     # [2B,K,9]
+    fps = graphs.pack.nodes_idx_m                                          # node rows in the packed (Morton) order: the node table
+    deformations = deformer.forward_fused(fsrc, ftgt, idx_self, idx_tgt, src, vt, sm, fps)     # [2B,K,9]  comes out in that order
     # identity offset + 6D -> R (models/loss.py:1258-1264) + skinning + ARAP (:1269-1273); the smoothness term is never used
     deformed, arap, _ = deform_from_d9(src, graphs, deformations)
     cd_d1, cd_d2, _, _ = ops.chamfer_fwd(deformed, tgt)                    # chamfer(deformed, target)   :1279

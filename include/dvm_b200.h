@@ -163,25 +163,29 @@ int dvm_arap_bwd(const float* xyz, const int64_t* nodes_idx, const int64_t* ring
 
 /* ------------------------------------------------------------------------------------------
  * HBM-shaped layout of the same forward (lib/deformation_graph_point.py:233-261): the product path.  The graph is
- * static per shape, so the host lays it out once (deformation_graph.build_graphs):
- *   table   f32[B][K][16]   node records, 64-byte aligned: R0..R8, t0..t2, g0..g2, 0   (g = xyz[nodes_idx])
- *   vorder  int32[B][N]     vertices in Morton order;  s_infl int32[B][3][N], s_w f32[B][3][N]: influence lists of
- *                           vertex vorder[i], slot-major;  norder int32[B][K], s_ring int32[B][ring_k][K]: same for the ring;
- *   csr_ptr int32[B][K+1], csr_vert int32[B][3N], csr_w f32[B][3N]: vertices influenced by each node (ascending vertex id).
- * dvm_node_table packs (R, t, g); dvm_node_table_from_d9 fuses models/loss.py:1257-1264 + rotation_6d_to_matrix (39-45):
- *   d9[B][K][9] = Deformer output, t = d9[0:3], R = rot6d(d9[3:9] + [1,0,0,0,1,0]); R_out/t_out optional plain copies.
- * dvm_skin_fwd_packed == dvm_skin_fwd, dvm_arap_fwd_packed == dvm_arap_fwd (sr may be NULL: smoothness skipped),
- * dvm_skin_bwd_csr == dvm_skin_bwd without atomics (deterministic; dR, dt OVERWRITTEN).
+ * static per shape, so the host lays it out once (deformation_graph.pack_graph).  NODES ARE RENUMBERED in Morton order of
+ * their positions: node_perm int32[B][K], node_perm[new] = old (the reference's FPS order).
+ *   table   f32[B][K][16]   node records in the NEW order, 64-byte aligned: R0..R8, t0..t2, g0..g2, 0   (g = node position)
+ *   vorder  int32[B][N]     vertices in Morton order;  s_xyz f32[B][N][3] their coordinates;  s_infl int32[B][3][N] (new node
+ *                           numbers), s_w f32[B][3][N]: influence lists of vertex vorder[i], slot-major;
+ *   s_ring  int32[B][ring_k][K]: ring of new node i (new numbers), slot-major;
+ *   csr_ptr int32[B][K+1], csr_vert int32[B][3N], csr_w f32[B][3N]: vertices influenced by each new node (ascending vertex id).
+ * dvm_node_table packs (R, t, g): R[B][K][9], t[B][K][3] rows are read through node_perm when it is non-NULL (inputs in the
+ * reference's node order), directly otherwise (inputs already in the new order); nodes_xyz[B][K][3] is in the new order.
+ * dvm_node_table_from_d9 fuses models/loss.py:1257-1264 + rotation_6d_to_matrix (39-45): d9[B][K][9] = Deformer output,
+ *   t = d9[0:3], R = rot6d(d9[3:9] + [1,0,0,0,1,0]); R_out/t_out optional plain copies (new order).
+ * dvm_skin_fwd_packed == dvm_skin_fwd (out[B][N][3] in the ORIGINAL vertex order), dvm_arap_fwd_packed == dvm_arap_fwd (sr may
+ * be NULL: smoothness skipped), dvm_skin_bwd_csr == dvm_skin_bwd without atomics (deterministic; dR, dt OVERWRITTEN, new order).
  * ------------------------------------------------------------------------------------------ */
-int dvm_node_table(const float* R, const float* t, const float* nodes_xyz, int B, int K, float* table, void* stream);
-int dvm_node_table_from_d9(const float* d9, const float* nodes_xyz, int B, int K, float* table,
+int dvm_node_table(const float* R, const float* t, const float* nodes_xyz, const int32_t* node_perm, int B, int K, float* table, void* stream);
+int dvm_node_table_from_d9(const float* d9, const float* nodes_xyz, const int32_t* node_perm, int B, int K, float* table,
                            float* R_out, float* t_out, void* stream);
-int dvm_skin_fwd_packed(const float* xyz, const int32_t* vorder, const int32_t* s_infl, const float* s_w,
+int dvm_skin_fwd_packed(const float* s_xyz, const int32_t* vorder, const int32_t* s_infl, const float* s_w,
                         const float* table, int B, int N, int K, float* out, void* stream);
 int dvm_skin_bwd_csr(const float* xyz, const float* nodes_xyz, const int32_t* csr_ptr, const int32_t* csr_vert,
                      const float* csr_w, const float* dOut, int B, int N, int K, float* dR, float* dt, void* stream);
 size_t dvm_arap_packed_workspace_bytes(int B, int K);
-int dvm_arap_fwd_packed(const int32_t* norder, const int32_t* s_ring, const float* table, int B, int K, int ring_k,
+int dvm_arap_fwd_packed(const int32_t* s_ring, const float* table, int B, int K, int ring_k,
                         float* arap, float* sr, void* ws, size_t ws_bytes, void* stream);
 
 /* index_points + Conv2d(k->1, 1x1) over the neighbour axis, fused (models/loss.py:1252-1253 feeding

@@ -169,7 +169,7 @@ def test_match_deform_at_benchmarked_sizes(n, pairs):
         assert perr <= F16_W_BOUND, perr
         _report("match_deform_scale", n=n, problem=p, piv_err=perr, unresolvable_rows=int((~res).sum()))
     # deform half
-    d9 = out["deformations"].cpu()
+    d9 = graphs.pack.to_old_order(out["deformations"]).cpu()             # rows follow the packed (Morton) node order
     deformed = out["deformed"].cpu()
     for p in range(2 * pairs):
         warped, arap, _ = _deform_oracle(src[p], graphs, d9[p], p)
@@ -264,11 +264,19 @@ def test_packed_deform_kernels_match_reference_layout_kernels(golden_graph):
     iden = torch.tensor([1.0, 0, 0, 0, 1, 0])
     R = ops.rot6d_fwd((d9g[..., 3:] + iden.cuda()).contiguous())
     t = d9g[..., :3].contiguous()
-    # tables: fused == unfused, bit for bit
-    tb1 = ops.node_table(R, t, graphs.pack.nodes_xyz)
-    tb2, R2, t2 = ops.node_table_from_d9(d9g, graphs.pack.nodes_xyz, want_rt=True)
-    assert torch.equal(tb1, tb2) and torch.equal(R, R2) and torch.equal(t, t2)
-    assert torch.equal(tb1[..., :9].reshape(B, K, 3, 3), R) and torch.equal(tb1[..., 9:12], t) and torch.equal(tb1[..., 12:15], graphs.pack.nodes_xyz)
+    # tables (R, t, d9 are in the reference's node order here: read through node_perm): fused == unfused, bit for bit
+    pk = graphs.pack
+    tb1 = ops.node_table(R, t, pk.nodes_xyz, node_perm=pk.node_perm)
+    tb2, R2, t2 = ops.node_table_from_d9(d9g, pk.nodes_xyz, want_rt=True, node_perm=pk.node_perm)
+    no = pk.node_perm.long()
+    R_new = torch.gather(R, 1, no[..., None, None].expand(B, K, 3, 3))
+    t_new = torch.gather(t, 1, no[..., None].expand(B, K, 3))
+    assert torch.equal(tb1, tb2) and torch.equal(R_new, R2) and torch.equal(t_new, t2)
+    assert torch.equal(tb1[..., :9].reshape(B, K, 3, 3), R_new) and torch.equal(tb1[..., 9:12], t_new) and torch.equal(tb1[..., 12:15], pk.nodes_xyz)
+    assert torch.equal(pk.to_old_order(R2), R) and torch.equal(torch.gather(graphs.nodes_idx, 1, no), pk.nodes_idx_m)
+    # inputs already in the packed order (what the pipeline does): same table
+    tb3 = ops.node_table_from_d9(torch.gather(d9g, 1, no[..., None].expand(B, K, 9)).contiguous(), pk.nodes_xyz)
+    assert torch.equal(tb3, tb1)
     # forward: packed vs reference-layout kernels vs oracle
     w_old = ops.skin_fwd(vg, graphs.nodes_idx, graphs.influence, graphs.weights, R, t)
     a_old, s_old = ops.arap_fwd(vg, graphs.nodes_idx, graphs.ring, R, t)
@@ -284,7 +292,7 @@ def test_packed_deform_kernels_match_reference_layout_kernels(golden_graph):
         assert (w_new[p].cpu() - warped[0]).abs().max().item() <= RTOL * verts[p].abs().max().item()
         assert abs(a_new[p].item() - arap.item()) <= RTOL * abs(arap.item())
         assert abs(s_new[p].item() - sr.item()) <= RTOL * abs(sr.item())
-    wf, af, _ = deform_from_d9(vg, graphs, d9g)
+    wf, af, _ = deform_from_d9(vg, graphs, d9g, packed_order=False)
     assert torch.equal(wf, w_new) and torch.equal(af, a_new)
     # backward: node-major CSR kernel vs the atomic kernel (sum order differs) vs fp64
     go = torch.randn(B, n, 3, generator=gen)
@@ -292,9 +300,10 @@ def test_packed_deform_kernels_match_reference_layout_kernels(golden_graph):
     dR_new, dt_new = ops.skin_bwd_csr(vg, graphs.pack, go.cuda())
     dR_again, dt_again = ops.skin_bwd_csr(vg, graphs.pack, go.cuda())
     assert torch.equal(dR_new, dR_again) and torch.equal(dt_new, dt_again)          # deterministic
+    dR_new, dt_new = pk.to_old_order(dR_new), pk.to_old_order(dt_new)               # packed -> reference node order
     infl = graphs.influence.cpu()
     wts = graphs.weights.cpu().double()
-    nodes_xyz = graphs.pack.nodes_xyz.cpu().double()
+    nodes_xyz = pk.to_old_order(pk.nodes_xyz).cpu().double()
     for p in range(B):
         ref_t = torch.zeros(K, 3, dtype=torch.float64)
         ref_R = torch.zeros(K, 9, dtype=torch.float64)
