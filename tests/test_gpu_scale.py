@@ -185,7 +185,7 @@ def test_match_deform_at_benchmarked_sizes(n, pairs):
             errs = {}
             for name, pts in (("cd_deform", out["deformed"][p:p + 1]), ("cd_self", out["verts_t"][p:p + 1])):
                 g1, g2, _, _ = ops.chamfer_fwd(pts, tg)
-                assert torch.equal((g1.mean(1) + g2.mean(1))[0], out[name][p])
+                assert torch.allclose((g1.mean(1) + g2.mean(1))[0], out[name][p], rtol=1e-6)      # same kernel; the mean is reduced in another batch shape
                 rows = _sample_rows(n, 1024, 77)
                 c1, _, i1, _ = og.chamfer_3d(pts.cpu()[:, rows], tgt[p:p + 1])
                 _, c2, _, _ = og.chamfer_3d(pts.cpu(), tgt[p:p + 1][:, rows]) if n <= 20000 else (None, None, None, None)
