@@ -55,6 +55,11 @@ SIGNATURES = {
     "dvm_arap_fwd_packed": (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "dvm_gather_conv_fwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 2),
     "dvm_gather_conv_bwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 4),
+    "dvm_topk_select": (c_int, [c_void_p, ctypes.c_longlong, c_int, ctypes.c_longlong, c_int, c_void_p, c_void_p]),
+    "dvm_pair_dist_fwd": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dvm_pair_dist_bwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p, c_void_p]),
+    "dvm_gather_rows_fwd": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "dvm_gather_rows_bwd": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
     "dvm_linear_act_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

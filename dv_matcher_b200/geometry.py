@@ -25,14 +25,17 @@ def knn_grad(x, y, k):
 
 
 def knn(a, b, k, chunk=4096):
-    """Feature-space k-NN by -||a-b||^2 in the reference's hand-written GEMM form (models/loss.py:451-462).
+    """Feature-space k-NN by -||a-b||^2 in the reference's hand-written GEMM form (models/loss.py:451-462), int64 [B,S,k]
+    in descending score order like `topk`.
 
-    Large k (500/300 for the 1000 sampled queries of the dist loss, models/loss.py:1367,1380) is the
-    "next" row f2 of SURVEY section 8: until a native large-k selection kernel lands this runs as stock torch
-    ops ON THE GPU, row-chunked so no [B,N,M] matrix outlives a chunk.
-    """
+    k <= 10: the fused similarity kernel (exact distances).  Larger k (500 / 300 for the 1000 sampled queries of the dist loss,
+    models/loss.py:1367,1380): the scores 2 a.b - |b|^2 on tcgen05 (3xTF32, fp32-equivalent) + dvm_topk_select (radix selection
+    of the k best per row, one CTA per row).  Rows that are too long for the GEMM's bias staging are scored in column chunks by
+    stock matmul and selected by the same kernel."""
     if k <= 10 and a.shape[-1] % 4 == 0:
         return ops.softmap_fwd(a, b, None, topk=k, soft=False, prec="fp32").top_idx.long()
+    if a.is_cuda and a.shape[-1] % 4 == 0 and k <= 1024 and b.shape[1] <= 32768:
+        return ops.knn_feature_large(a.detach(), b.detach(), k)
     bb = torch.sum(b ** 2, dim=2, keepdim=True).transpose(2, 1)
     out = []
     for s in range(0, a.shape[1], chunk):
@@ -43,12 +46,53 @@ def knn(a, b, k, chunk=4096):
     return torch.cat(out, dim=1)
 
 
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx2):
+        ctx.save_for_backward(idx2)
+        ctx.n = points.shape[1]
+        return ops.gather_rows_fwd(points, idx2)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (idx2,) = ctx.saved_tensors
+        return ops.gather_rows_bwd(d_out.contiguous(), idx2, ctx.n), None
+
+
 def index_points(points, idx):
-    """[B,N,C] gathered by idx [B,S,K] -> [B,S,K,C] (models/loss.py:464-473)."""
+    """[B,N,C] gathered by idx [B,S,K] -> [B,S,K,C] (models/loss.py:464-473): dvm_gather_rows_fwd/bwd."""
     raw_shape = idx.shape
-    idx = idx.reshape(raw_shape[0], -1)
-    res = torch.gather(points, 1, idx[..., None].expand(-1, -1, points.shape[-1]))
+    idx2 = idx.reshape(raw_shape[0], -1).contiguous()
+    if not points.is_cuda or points.dtype != torch.float32:
+        res = torch.gather(points, 1, idx2[..., None].expand(-1, -1, points.shape[-1]))
+    else:
+        res = _GatherRows.apply(points.contiguous(), idx2.long())
     return res.view(*raw_shape, -1)
+
+
+class _PairDist(torch.autograd.Function):
+    """(feat [B,N,C], q [S], nbr [B,S,k]) -> |feat[nbr] - feat[q]| [B,S,k]; geo gathered alongside when given."""
+
+    @staticmethod
+    def forward(ctx, feat, qidx, nbr, geo):
+        feat = feat.float().contiguous()
+        d, g = ops.pair_dist_fwd(feat, qidx, nbr, geo)
+        ctx.save_for_backward(feat, qidx, nbr, d)
+        if g is None:
+            g = torch.empty(0, device=feat.device)
+        ctx.mark_non_differentiable(g)
+        return d, g
+
+    @staticmethod
+    def backward(ctx, gd, _gg):
+        feat, qidx, nbr, d = ctx.saved_tensors
+        return ops.pair_dist_bwd(feat, qidx, nbr, d, gd.contiguous()), None, None, None
+
+
+def pair_dist(feat, qidx, nbr, geo=None):
+    """torch.norm(index_points(feat, nbr) - feat[:, qidx][:, :, None, :], dim=-1) and geo[b, nbr, qidx] (models/loss.py:1366-1378)."""
+    d, g = _PairDist.apply(feat, qidx.long().contiguous(), nbr.long().contiguous(), geo)
+    return d, (g if geo is not None else None)
 
 
 def index_points_idx(points, idx):

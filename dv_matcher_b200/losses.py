@@ -58,13 +58,15 @@ def dist_loss_term(feat, dist, n_sample, k, numbers=None):
         numbers = random.sample(range(num), n_sample)
     rn = torch.as_tensor(numbers, device=feat.device, dtype=torch.long)
     f1 = feat[:, rn]                                               # [B,S,C]
-    idx = knn(f1, feat, k)                                         # [B,S,k]
-    # ||feat[idx] - f1||: the reference gathers f2 = index_points(feat, idx) ([B,S,k,C], 256 MB per shape at S=1000,
-    # k=500) and takes the norm; the same direct-difference distances are a gather from the [B,S,N] distance matrix
-    dist_result = torch.gather(torch.cdist(f1, feat, compute_mode="donot_use_mm_for_euclid_dist"), 2, idx)   # [B,S,k]
-    # dist[i, idx[i], idx_num[i]]: one batched gather instead of the reference's Python loop over B
-    bidx = torch.arange(B, device=feat.device)[:, None, None]
-    dist_f = dist[bidx, idx, rn[None, :, None]].float()            # torch.zeros_like(idx, dtype=float) in the reference
+    idx = knn(f1, feat, k)                                         # [B,S,k]  tcgen05 scores + radix selection (dvm_topk_select)
+    if feat.is_cuda and feat.shape[-1] % 4 == 0 and dist.is_contiguous() and dist.dtype in (torch.float32, torch.float64):
+        # ||feat[idx] - f1|| and dist[i, idx[i], idx_num[i]] in one gather kernel with its own backward: the reference builds
+        # f2 = index_points(feat, idx) ([B,S,k,C]: 256 MB per shape at S = 1000, k = 500) and loops over B in Python
+        dist_result, dist_f = geometry.pair_dist(feat, rn, idx, dist)
+    else:
+        dist_result = torch.gather(torch.cdist(f1, feat, compute_mode="donot_use_mm_for_euclid_dist"), 2, idx)   # [B,S,k]
+        bidx = torch.arange(B, device=feat.device)[:, None, None]
+        dist_f = dist[bidx, idx, rn[None, :, None]].float()        # torch.zeros_like(idx, dtype=float) in the reference
     return torch.sum(1 - torch.abs(torch.nn.functional.cosine_similarity(dist_result, dist_f, dim=2)))
 
 

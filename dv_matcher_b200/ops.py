@@ -372,3 +372,83 @@ def linear_act_fwd(x, weight, bias, act="none", x_cols=None):
     check(lib.dvm_linear_act_fwd(x2.data_ptr(), x2.shape[0], K, x2.stride(0), w.data_ptr(), w.stride(0), ptr(b), N, {"none": 0, "elu": 1}[act],
                                  ptr(out), N, stream_ptr()), "dvm_linear_act_fwd")
     return out.reshape(*lead, N)
+
+
+def topk_select(scores, k, n_valid=None):
+    """Indices of the k largest entries of every row of scores [R, pitch] (first n_valid columns), descending, int64 [R,k]."""
+    lib = _lib.load()
+    require_device(scores)
+    if scores.dtype != torch.float32 or scores.dim() != 2 or scores.stride(1) != 1:
+        raise RuntimeError("topk_select: scores must be a float32 [rows, pitch] matrix with unit column stride")
+    R = scores.shape[0]
+    N = scores.shape[1] if n_valid is None else n_valid
+    idx = torch.empty(R, k, dtype=torch.int64, device=scores.device)
+    check(lib.dvm_topk_select(scores.data_ptr(), R, N, scores.stride(0), int(k), ptr(idx), stream_ptr()), "dvm_topk_select")
+    return idx
+
+
+def knn_feature_large(a, b, k):
+    """knn(a, b, k) of models/loss.py:451-462 for k > 10: scores 2 a.b - |b|^2 on tcgen05 (3xTF32), radix selection of the k best."""
+    a, b = f32c(a), f32c(b)
+    B, S, C = a.shape
+    N = b.shape[1]
+    npad = (N + 3) // 4 * 4
+    out = torch.empty(B, S, k, dtype=torch.int64, device=a.device)
+    bias = (-0.5) * (b * b).sum(-1)                                    # [B,N]
+    for i in range(B):
+        sc = torch.empty(S, npad, dtype=torch.float32, device=a.device)
+        lib = _lib.load()
+        check(lib.dvm_linear_act_fwd(a[i].data_ptr(), S, C, C, b[i].data_ptr(), C, ptr(bias[i].contiguous()), N, 0, ptr(sc), npad, stream_ptr()),
+              "dvm_linear_act_fwd")
+        out[i] = topk_select(sc, k, n_valid=N)
+    return out
+
+
+def pair_dist_fwd(feat, qidx, nbr, geo=None):
+    """d [B,S,k] = |feat[b, nbr] - feat[b, qidx]| (+ geo[b, nbr, qidx] as float32 when a [B,N,N] matrix is given)."""
+    lib = _lib.load()
+    feat = f32c(feat)
+    require_device(feat)
+    B, N, C = feat.shape
+    S, k = nbr.shape[1], nbr.shape[2]
+    d = torch.empty(B, S, k, dtype=torch.float32, device=feat.device)
+    g_out = None
+    if geo is not None:
+        if geo.dtype not in (torch.float32, torch.float64) or tuple(geo.shape) != (B, N, N) or not geo.is_contiguous():
+            raise RuntimeError("pair_dist_fwd: geo must be a contiguous float32/float64 [B,N,N] tensor")
+        g_out = torch.empty_like(d)
+    check(lib.dvm_pair_dist_fwd(ptr(feat), ptr(qidx, torch.int64), ptr(nbr, torch.int64), B, N, C, S, k, ptr(d),
+                                ptr(geo), int(geo is not None and geo.dtype == torch.float64), ptr(g_out), stream_ptr()), "dvm_pair_dist_fwd")
+    return d, g_out
+
+
+def pair_dist_bwd(feat, qidx, nbr, d, g):
+    lib = _lib.load()
+    feat, d, g = f32c(feat), f32c(d), f32c(g)
+    B, N, C = feat.shape
+    S, k = nbr.shape[1], nbr.shape[2]
+    dfeat = torch.zeros_like(feat)
+    check(lib.dvm_pair_dist_bwd(ptr(feat), ptr(qidx, torch.int64), ptr(nbr, torch.int64), ptr(d), ptr(g), B, N, C, S, k, ptr(dfeat), stream_ptr()),
+          "dvm_pair_dist_bwd")
+    return dfeat
+
+
+def gather_rows_fwd(points, idx2):
+    """points [B,N,C], idx2 int64 [B,R] -> [B,R,C]."""
+    lib = _lib.load()
+    points = f32c(points)
+    require_device(points)
+    B, N, C = points.shape
+    R = idx2.shape[1]
+    out = torch.empty(B, R, C, dtype=torch.float32, device=points.device)
+    check(lib.dvm_gather_rows_fwd(ptr(points), ptr(idx2, torch.int64), B, N, R, C, ptr(out), stream_ptr()), "dvm_gather_rows_fwd")
+    return out
+
+
+def gather_rows_bwd(d_out, idx2, N):
+    lib = _lib.load()
+    d_out = f32c(d_out)
+    B, R, C = d_out.shape
+    d_pts = torch.zeros(B, N, C, dtype=torch.float32, device=d_out.device)
+    check(lib.dvm_gather_rows_bwd(ptr(d_out), ptr(idx2, torch.int64), B, N, R, C, ptr(d_pts), stream_ptr()), "dvm_gather_rows_bwd")
+    return d_pts

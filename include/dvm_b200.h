@@ -197,6 +197,26 @@ int dvm_gather_conv_fwd(const float* feat, const int64_t* idx, const float* W, c
 int dvm_gather_conv_bwd(const float* feat, const int64_t* idx, const float* W, const float* dOut,
                         int B, int N, int R, int C, int k, float* dFeat, float* dW, float* dBias, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Large-k feature-space k-NN, the gathered distances of the dist loss and index_points.
+ * dvm_topk_select: per row of scores[rows][pitch] (N valid columns) the indices of the k largest scores, descending score,
+ *   ties -> lower index, k <= 1024.  Second half of knn(a, b, k) models/loss.py:451-462 for k = 500 / 300 (:1367, :1380): the
+ *   scores 2 a.b - |b|^2 come from dvm_linear_act_fwd (x = a, W = b, bias = -|b|^2 / 2; tcgen05, fp32-equivalent).
+ * dvm_pair_dist_fwd: d[b,s,t] = | feat[b, nbr[b,s,t]] - feat[b, qidx[s]] |_2  == torch.norm(index_points(feat, idx) -
+ *   f1[:, :, None, :], dim=-1) of models/loss.py:1368-1369 without the [B,S,k,C] tensor; geo (may be NULL; fp32 or fp64
+ *   [B][N][N], geo_is_f64) additionally gathers geo_out[b,s,t] = geo[b, nbr[b,s,t], qidx[s]] (:1370-1378, the Python loop over B).
+ * dvm_pair_dist_bwd: ACCUMULATES d/dfeat of sum g*d into dfeat[B][N][C] (vector atomics; 0 where d = 0 like torch.norm).
+ * dvm_gather_rows_fwd/bwd: index_points models/loss.py:464-473: out[b,r,:] = pts[b, idx[b,r], :] (idx flattened to [B][R]);
+ *   bwd ACCUMULATES into d_pts.
+ * ------------------------------------------------------------------------------------------ */
+int dvm_topk_select(const float* scores, long long rows, int N, long long pitch, int k, int64_t* idx, void* stream);
+int dvm_pair_dist_fwd(const float* feat, const int64_t* qidx, const int64_t* nbr, int B, int N, int C, int S, int k,
+                      float* d, const void* geo, int geo_is_f64, float* geo_out, void* stream);
+int dvm_pair_dist_bwd(const float* feat, const int64_t* qidx, const int64_t* nbr, const float* d, const float* g,
+                      int B, int N, int C, int S, int k, float* dfeat, void* stream);
+int dvm_gather_rows_fwd(const float* pts, const int64_t* idx, int B, int N, int R, int C, float* out, void* stream);
+int dvm_gather_rows_bwd(const float* d_out, const int64_t* idx, int B, int N, int R, int C, float* d_pts, void* stream);
+
 /* One layer of the Deformer's decoder MLP (models/model.py:433-452: nn.Linear + nn.ELU; called at :476-477):
  *   out[r, n] = act( sum_k x[r,k] W[n,k] + bias[n] ),  x[rows][x_pitch] (K used), W[N][w_pitch] (nn.Linear layout),
  *   act 0 = identity, 1 = ELU(alpha=1).  tcgen05 tensor cores with 3xTF32 operand splitting (fp32-equivalent: relative

@@ -1,0 +1,129 @@
+"""GPU parity of the large-k selection, the gathered pair distances of the dist loss and index_points.
+
+Reference semantics: knn models/loss.py:451-462 (k = 500 / 300 at :1367, :1380), dist loss :1351-1396, index_points :464-473."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as og
+
+pytestmark = pytest.mark.gpu
+
+
+def test_topk_select_matches_torch_topk_including_ties():
+    from dv_matcher_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    for rows, n, k in ((7, 4995, 500), (3, 300, 300), (5, 1031, 17), (2, 20000, 1024), (4, 64, 1)):
+        s = torch.randn(rows, n, generator=gen)
+        s[0, : n // 3] = 0.25                                   # a long run of exact ties across the selection boundary
+        s[1 % rows, 5] = float("-inf")
+        sg = s.cuda()
+        idx = ops.topk_select(sg, k).cpu()
+        ref = torch.sort(s, dim=1, descending=True, stable=True)            # stable: ties -> lower index first
+        assert torch.equal(torch.gather(s, 1, idx), ref.values[:, :k])
+        assert torch.equal(idx, ref.indices[:, :k])
+    # pitched view (padded rows)
+    sp = torch.randn(6, 1000, generator=gen).cuda()
+    idx = ops.topk_select(sp, 50, n_valid=997).cpu()
+    assert torch.equal(idx, torch.sort(sp[:, :997].cpu(), dim=1, descending=True, stable=True).indices[:, :50])
+
+
+@pytest.mark.parametrize("k,S", [(500, 1000), (300, 500), (37, 64)])
+def test_knn_large_k_matches_reference_form(k, S):
+    """geometry.knn (tcgen05 3xTF32 scores + radix selection) against oracle.geometry.knn_feature (the reference's GEMM form):
+    identical neighbour SETS wherever the rank-k / rank-k+1 score gap exceeds fp32 GEMM rounding."""
+    from dv_matcher_b200 import geometry, synthetic
+    d = synthetic.make_batch(2, 4995, 4995)
+    feat = d["feat1"]
+    rn = torch.randperm(4995, generator=torch.Generator().manual_seed(k))[:S]
+    a = feat[:, rn]
+    got = geometry.knn(a.cuda(), feat.cuda(), k).cpu()
+    assert got.shape == (2, S, k) and got.dtype == torch.int64
+    a64, b64 = a.double(), feat.double()
+    sc = 2 * a64 @ b64.transpose(1, 2) - (b64 ** 2).sum(-1)[:, None, :]
+    ss, order = torch.sort(sc, dim=-1, descending=True, stable=True)
+    gap = ss[..., k - 1] - ss[..., k]
+    scale = ss[..., 0].abs().clamp_min(1.0)
+    clear = gap > 2e-6 * scale
+    assert clear.float().mean() > 0.95
+    got_sorted = torch.sort(got, dim=-1).values
+    ref_sorted = torch.sort(order[..., :k], dim=-1).values
+    assert torch.equal(got_sorted[clear], ref_sorted[clear])
+    # and the order is the score order (descending), as topk returns it
+    gs = torch.gather(sc, 2, got)
+    assert (gs[..., :-1] >= gs[..., 1:] - 2e-6 * scale[..., None]).all()
+    # the reference's own fp32 form agrees on the same rows
+    ref32 = og.knn_feature(a, feat, k)
+    assert torch.equal(torch.sort(ref32, dim=-1).values[clear], ref_sorted[clear])
+
+
+def test_pair_dist_forward_backward_and_geodesic_gather():
+    from dv_matcher_b200 import geometry
+    gen = torch.Generator().manual_seed(9)
+    B, N, C, S, k = 2, 700, 128, 90, 33
+    feat = torch.randn(B, N, C, generator=gen) * 0.4
+    rn = torch.randperm(N, generator=gen)[:S]
+    nbr = torch.randint(0, N, (B, S, k), generator=gen)
+    nbr[:, :, 0] = rn[None, :]                                   # the query itself: d = 0 -> zero gradient (torch.norm)
+    geo64 = torch.rand(B, N, N, generator=gen, dtype=torch.float64)
+    coef = torch.randn(B, S, k, generator=gen)
+    # reference (models/loss.py:1366-1378) in fp64
+    fd = feat.double().requires_grad_(True)
+    f2 = og.index_points(fd, nbr)
+    dref = torch.norm(f2 - fd[:, rn][:, :, None, :], dim=-1)
+    (dref * coef.double()).sum().backward()
+    gref = torch.stack([geo64[i, nbr[i].reshape(-1), rn.repeat_interleave(k)] for i in range(B)]).reshape(B, S, k)
+    for geo in (geo64, geo64.float()):
+        fg = feat.cuda().requires_grad_(True)
+        dgot, ggot = geometry.pair_dist(fg, rn.cuda(), nbr.cuda(), geo.cuda())
+        np.testing.assert_allclose(dgot.detach().cpu().numpy(), dref.detach().float().numpy(), rtol=2e-6, atol=1e-6)
+        np.testing.assert_array_equal(ggot.cpu().numpy(), gref.float().numpy() if geo.dtype == torch.float64 else geo[torch.arange(B)[:, None, None], nbr, rn[None, :, None]].numpy())
+        (dgot * coef.cuda()).sum().backward()
+        err = (fg.grad.cpu().double() - fd.grad).abs().max().item() / fd.grad.abs().max().item()
+        assert err <= 1e-5, err
+    d_only, none = geometry.pair_dist(feat.cuda(), rn.cuda(), nbr.cuda())
+    assert none is None and torch.equal(d_only, dgot.detach())
+
+
+@pytest.mark.parametrize("C", [3, 128, 30])
+def test_index_points_forward_backward(C):
+    from dv_matcher_b200 import geometry
+    gen = torch.Generator().manual_seed(C)
+    B, N, S, K = 2, 333, 50, 10
+    pts = torch.randn(B, N, C, generator=gen)
+    idx = torch.randint(0, N, (B, S, K), generator=gen)
+    pg = pts.cuda().requires_grad_(True)
+    out = geometry.index_points(pg, idx.cuda())
+    assert out.shape == (B, S, K, C) and torch.equal(out.detach().cpu(), og.index_points(pts, idx))
+    go = torch.randn(B, S, K, C, generator=gen)
+    out.backward(go.cuda())
+    ref = torch.zeros(B, N, C, dtype=torch.float64)
+    for b in range(B):
+        ref[b].index_add_(0, idx[b].reshape(-1), go[b].reshape(-1, C).double())
+    assert (pg.grad.cpu().double() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0)
+
+
+def test_dist_loss_term_matches_reference_formula():
+    """losses.dist_loss_term (kernels) against the reference's statement sequence evaluated in torch fp64 on the CPU."""
+    from dv_matcher_b200 import losses, synthetic
+    d = synthetic.make_batch(2, 2000, 2000)
+    feat = d["feat1"]
+    dist = torch.cdist(d["xyz1"].double(), d["xyz1"].double())
+    numbers = torch.randperm(2000, generator=torch.Generator().manual_seed(3))[:300].tolist()
+    k = 120
+    fg = feat.cuda().requires_grad_(True)
+    got = losses.dist_loss_term(fg, dist.cuda(), 300, k, numbers)
+    got.backward()
+    fd = feat.double().requires_grad_(True)
+    rn = torch.tensor(numbers)
+    f1 = fd[:, rn]
+    idx = og.knn_feature(f1.float(), fd.float(), k)                      # the reference's fp32 selection
+    f2 = og.index_points(fd, idx)
+    dr = torch.norm(f2 - f1[:, :, None, :], dim=-1)
+    df = torch.stack([dist[i, idx[i].reshape(-1), rn.repeat_interleave(k)] for i in range(2)]).reshape(2, 300, k).float().double()
+    ref = torch.sum(1 - torch.abs(torch.nn.functional.cosine_similarity(dr, df, dim=2)))
+    ref.backward()
+    assert abs(got.item() - ref.item()) <= 2e-4 * abs(ref.item()), (got.item(), ref.item())
+    g, r = fg.grad.cpu().double(), fd.grad
+    cos = float((g * r).sum() / (g.norm() * r.norm()))
+    assert cos >= 0.9999 and abs(float(g.norm() / r.norm()) - 1) <= 1e-3, (cos, float(g.norm() / r.norm()))
