@@ -77,3 +77,45 @@ def gather_pair_results(local_results, world=None):
     out = [None] * world
     dist.all_gather_object(out, local_results)
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# one giant pair (config 5, N = M = 200k): rows shard, columns replicate, nothing is exchanged on the data path
+# --------------------------------------------------------------------------------------------------
+def shard_rows(n_rows, rank, world):
+    """[lo, hi) of the contiguous row slab rank `rank` owns (balanced to within one row)."""
+    base, extra = divmod(n_rows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def match_rows_sharded(feat1, feat2, verts2, alpha=100.0, rank=None, world=None, prec=None, gather=False, soft_map_fn=None):
+    """Direction 1 -> 2 of ONE pair with the source rows sharded over the ranks: every rank holds all of
+    feat2 / verts2 (102 MB + 2.4 MB at 200k: replicated), takes its slab of feat1 rows and runs the fused kernel on it --
+    row softmax, top-10, arg-min and Pi @ verts2 need no exchange.  The reverse direction is the same call with the
+    roles swapped.  feat1 [1,N,C], feat2 [1,M,C], verts2 [1,M,3].
+
+    Returns dict(rows=(lo, hi), argmin, top_idx, top_w, verts_t) for the local slab; with gather=True every entry is
+    all-gathered into the full [1,N,...] result (row order preserved; a host-side convenience, not part of the data path)."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if soft_map_fn is None:
+        from . import maps
+        soft_map_fn = maps.soft_map
+    lo, hi = shard_rows(feat1.shape[1], rank, world)
+    sm, vt = soft_map_fn(feat1[:, lo:hi].contiguous(), feat2, alpha, v=verts2, prec=prec)
+    out = dict(rows=(lo, hi), argmin=sm.argmin, top_idx=sm.idx, top_w=sm.w, verts_t=vt)
+    if gather and world > 1:
+        n = feat1.shape[1]
+        most = max(shard_rows(n, r, world)[1] - shard_rows(n, r, world)[0] for r in range(world))
+        for k in ("argmin", "top_idx", "top_w", "verts_t"):
+            t = out[k]
+            pad = torch.zeros(t.shape[0], most, *t.shape[2:], dtype=t.dtype, device=t.device)
+            pad[:, : hi - lo] = t
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            out[k] = torch.cat([parts[r][:, : shard_rows(n, r, world)[1] - shard_rows(n, r, world)[0]] for r in range(world)], dim=1)
+        out["rows"] = (0, n)
+    return out

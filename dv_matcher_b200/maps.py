@@ -165,10 +165,11 @@ class LazySoftMap(_MapBase):
 
     def topk(self, k=TOPK, prec=None):
         if prec is None:
-            # the backward re-uses the forward's row statistics: training takes the fp32 candidate pass (1e-4 parity
-            # of weights AND gradients) unless DVM_TRAIN_PREC says otherwise; inference keeps the tcgen05 pass
+            # training runs the tcgen05 pass too (indices, distances, row statistics are exact fp32 whatever the candidate pass;
+            # the full / partial loss tests against the unmodified reference pass with it); DVM_TRAIN_PREC=fp32 selects the
+            # CUDA-core candidate pass (1e-4 parity of the soft weights themselves)
             needs_grad = torch.is_grad_enabled() and (self.x.requires_grad or self.y.requires_grad)
-            prec = os.environ.get("DVM_TRAIN_PREC", "fp32") if needs_grad else _PRECISION
+            prec = os.environ.get("DVM_TRAIN_PREC", _PRECISION) if needs_grad else _PRECISION
         w, idx, argmin, top_d, rmin, rsum = _SoftMapTopK.apply(self.x.float().contiguous(), self.y.float().contiguous(),
                                                               self.alpha, k, prec)
         return SparseSoftMap(idx, w, self.shape[2], argmin, top_d, rmin, rsum)

@@ -316,3 +316,19 @@ def test_packed_deform_kernels_match_reference_layout_kernels(golden_graph):
         assert (dt_new[p].cpu().double() - ref_t).abs().max().item() <= 1e-5 * sc_t
         assert (dR_new[p].cpu().double().reshape(K, 9) - ref_R).abs().max().item() <= 1e-5 * sc_R
         assert (dt_old[p].cpu().double() - ref_t).abs().max().item() <= 1e-5 * sc_t
+
+
+def test_giant_pair_row_sharding_equals_unsharded():
+    """SURVEY 8e, one giant pair: the row slabs four ranks would compute (Y replicated, no exchange) concatenate to the
+    unsharded result -- indices bit for bit, weights to the run-to-run reproducibility of the 16-bit softmax mass."""
+    from dv_matcher_b200 import distributed as dd, maps, synthetic
+    n = 20000
+    d = synthetic.make_batch(1, n, n)
+    f1, f2, v2 = d["feat1"].cuda(), d["feat2"].cuda(), d["xyz2"].cuda()
+    full, vt = maps.soft_map(f1, f2, 100.0, v=v2)
+    parts = [dd.match_rows_sharded(f1, f2, v2, alpha=100.0, rank=r, world=4) for r in range(4)]
+    assert [p["rows"] for p in parts] == [(0, 5000), (5000, 10000), (10000, 15000), (15000, 20000)]
+    assert torch.equal(torch.cat([p["argmin"] for p in parts], 1), full.argmin)
+    assert torch.equal(torch.cat([p["top_idx"] for p in parts], 1), full.idx)
+    assert torch.allclose(torch.cat([p["top_w"] for p in parts], 1), full.w, rtol=2e-5, atol=1e-9)
+    assert torch.allclose(torch.cat([p["verts_t"] for p in parts], 1), vt, rtol=2e-5, atol=1e-7)

@@ -93,6 +93,53 @@ def test_gradient_allreduce_gloo_world2(tmp_path):
     assert [g["pairs"] for g in got["gathered"]] == [[0, 2], [1, 3]]
 
 
+def test_shard_rows_partition():
+    from dv_matcher_b200.distributed import shard_rows
+    for n in (1, 7, 200000, 199999):
+        for world in (1, 2, 3, 8):
+            spans = [shard_rows(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _giant_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from dv_matcher_b200 import distributed as dd
+    from dv_matcher_b200.maps import SparseSoftMap
+    from oracle import maps as om
+    dd.init(backend="gloo")
+
+    def cpu_soft_map(x, y, alpha, v=None, prec=None):          # the oracle stands in for the CUDA kernel in this host-logic test
+        s = om.softmap_sparse(x, y, alpha, v=v, dtype=torch.float32)
+        return SparseSoftMap(s["idx"].int(), s["w"], y.shape[1], s["argmin"]), s["piv"]
+
+    g = torch.Generator().manual_seed(0)
+    f1, f2, v2 = torch.randn(1, 203, 16, generator=g), torch.randn(1, 150, 16, generator=g), torch.randn(1, 150, 3, generator=g)
+    res = dd.match_rows_sharded(f1, f2, v2, alpha=5.0, gather=True, soft_map_fn=cpu_soft_map)
+    if rank == 0:
+        torch.save({k: v for k, v in res.items()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_giant_pair_row_sharding_gloo_world2(tmp_path):
+    """Rows shard, columns replicate: the gathered result of 2 ranks equals the single-process result (no data-path exchange)."""
+    from oracle import maps as om
+    out = str(tmp_path / "giant.pt")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_giant_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    g = torch.Generator().manual_seed(0)
+    f1, f2, v2 = torch.randn(1, 203, 16, generator=g), torch.randn(1, 150, 16, generator=g), torch.randn(1, 150, 3, generator=g)
+    s = om.softmap_sparse(f1, f2, 5.0, v=v2, dtype=torch.float32)
+    assert got["rows"] == (0, 203)
+    assert torch.equal(got["argmin"], s["argmin"]) and torch.equal(got["top_idx"].long(), s["idx"])
+    assert torch.allclose(got["top_w"], s["w"]) and torch.allclose(got["verts_t"], s["piv"])
+
+
 def test_sparse_soft_map_protocol_cpu():
     """SparseSoftMap's dense view and torch-function interception (no kernels: dense fallback for foreign shapes)."""
     from dv_matcher_b200.maps import SparseSoftMap, topk_pi
