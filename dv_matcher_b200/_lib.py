@@ -29,6 +29,8 @@ SIGNATURES = {
     "dvm_softmap_fwd": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_float] + [c_int] * 3 + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "dvm_softmap_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
     "dvm_softmap_bwd": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_float, c_int] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
+    "dvm_softmap_bwd_tc_workspace_bytes": (c_size_t, [c_int] * 4),
+    "dvm_softmap_bwd_tc": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_float, c_int] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "dvm_sparse_transfer_fwd": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_void_p]),
     "dvm_sparse_transfer_bwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 3),
     "dvm_knn3_workspace_bytes": (c_size_t, [c_int] * 3),

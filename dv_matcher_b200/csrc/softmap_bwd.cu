@@ -202,6 +202,14 @@ softmap_bwd_topk_kernel(const float* __restrict__ X, const float* __restrict__ Y
     }
 }
 
+int launch_softmap_bwd_topk(const float* X, const float* Y, int B, int N, int M, int C, float alpha, int topk, const int32_t* top_idx,
+                            const float* top_w, const float* top_d, const float* dW, float* dX, float* dY, cudaStream_t st) {
+    const int rows = B * N;
+    softmap_bwd_topk_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(X, Y, N, M, C, alpha, topk, top_idx, top_w, top_d, dW, rows, dX, dY);
+    DVM_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace dvm
 
 using namespace dvm;

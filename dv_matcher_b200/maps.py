@@ -43,6 +43,7 @@ class _SoftMapTopK(torch.autograd.Function):
         out = ops.softmap_fwd(x, y, None, alpha=alpha, topk=topk, soft=True, prec=prec)
         ctx.save_for_backward(x, y, out.top_idx, out.top_w, out.top_d, out.row_min, out.row_sum)
         ctx.alpha = float(alpha)
+        ctx.prec = os.environ.get("DVM_BWD_PREC", prec)          # the backward follows the forward's precision class
         ctx.mark_non_differentiable(out.top_idx, out.argmin, out.top_d, out.row_min, out.row_sum)
         return out.top_w, out.top_idx, out.argmin, out.top_d, out.row_min, out.row_sum
 
@@ -50,7 +51,7 @@ class _SoftMapTopK(torch.autograd.Function):
     def backward(ctx, d_w, *_unused):
         x, y, idx, w, d, rmin, rsum = ctx.saved_tensors
         saved = ops.SoftMapOut(None, idx, w, d, rmin, rsum, None, None)
-        dx, dy = ops.softmap_bwd(x, y, ctx.alpha, saved, d_w.contiguous())
+        dx, dy = ops.softmap_bwd(x, y, ctx.alpha, saved, d_w.contiguous(), prec=ctx.prec)
         return dx, dy, None, None, None
 
 

@@ -52,8 +52,9 @@ def softmap_fwd(x, y, v=None, alpha=100.0, topk=10, soft=True, prec=None, want_s
     return SoftMapOut(argmin, top_idx, top_w, top_d, row_min, row_sum, piv, stats)
 
 
-def softmap_bwd(x, y, alpha, out, d_w):
-    """Gradient of the kept top-k weights w.r.t. x and y (dvm_softmap_bwd). Returns (dx, dy)."""
+def softmap_bwd(x, y, alpha, out, d_w, prec="fp32"):
+    """Gradient of the kept top-k weights w.r.t. x and y. Returns (dx, dy).
+    prec "fp32": dvm_softmap_bwd (CUDA cores, exact form); "f16" / "bf16": dvm_softmap_bwd_tc (dense part on tcgen05; C <= 128)."""
     lib = _lib.load()
     x, y = f32c(x), f32c(y)
     B, N, C = x.shape
@@ -62,6 +63,14 @@ def softmap_bwd(x, y, alpha, out, d_w):
     d_w = f32c(d_w)
     dx = torch.empty_like(x)
     dy = torch.zeros_like(y)
+    if prec != "fp32" and C <= 128:
+        nbytes = lib.dvm_softmap_bwd_tc_workspace_bytes(B, N, M, C)
+        ws = _lib.workspace.get(nbytes, x.device, "softmap_bwd_tc")
+        rc = lib.dvm_softmap_bwd_tc(ptr(x), ptr(y), B, N, M, C, float(alpha), topk,
+                                    ptr(out.top_idx), ptr(out.top_w), ptr(out.top_d), ptr(out.row_min), ptr(out.row_sum), ptr(d_w),
+                                    ptr(dx), ptr(dy), ptr(ws), ws.numel(), stream_ptr())
+        check(rc, "dvm_softmap_bwd_tc")
+        return dx, dy
     nbytes = lib.dvm_softmap_bwd_workspace_bytes(B, N, M, C)
     ws = _lib.workspace.get(nbytes, x.device, "softmap_bwd")
     rc = lib.dvm_softmap_bwd(ptr(x), ptr(y), B, N, M, C, float(alpha), topk,

@@ -88,6 +88,16 @@ int dvm_softmap_bwd(const float* X, const float* Y, int B, int N, int M, int C, 
                     const float* row_min, const float* row_sum, const float* dW,
                     float* dX, float* dY, void* ws, size_t ws_bytes, void* stream);
 
+/* The same backward with the dense part on tensor cores (tcgen05, f16 operands, fp32 accumulation in TMEM): per tile
+ * S = X~ Y~^T -> G = alpha c_i P_ij / d_ij (f16, written to shared memory as the next MMA's operand) -> dX += G Y~, dY += G^T X~;
+ * the exact 10-sparse top-k part is shared with dvm_softmap_bwd.  C <= 128.  dX, dY are OVERWRITTEN.  Stated bound on the
+ * gradient: 1e-2 relative to its largest entry (measured ~2e-3; the fp32 version above keeps 2e-4). */
+size_t dvm_softmap_bwd_tc_workspace_bytes(int B, int N, int M, int C);
+int dvm_softmap_bwd_tc(const float* X, const float* Y, int B, int N, int M, int C, float alpha, int topk,
+                       const int32_t* top_idx, const float* top_w, const float* top_d,
+                       const float* row_min, const float* row_sum, const float* dW,
+                       float* dX, float* dY, void* ws, size_t ws_bytes, void* stream);
+
 /* 10-sparse transfers Pi @ Y for any row width D: torch.matmul(Pi_12, feat2) models/model.py:471,
  * einsum('bij,bjkm->bikm') models/loss.py:1237 (with Y viewed as [B,M,k*m]).
  * out[b,i,:] = sum_k w[b,i,k] * Y[b, idx[b,i,k], :].   bwd: dW = <dOut, Y[idx]>, dY += w * dOut. */

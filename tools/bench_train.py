@@ -158,7 +158,7 @@ def run(args):
         line = dict(
             metric=METRIC.replace("match+deform", "training step: loss fwd+bwd + gradient all-reduce + Adam"), value=B * world * args.steps / (ms * 1e-3),
             unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
-            scaling="weak", vs_baseline=None, dtype=f"{prec} soft-map forward (tcgen05) + fp32 backward" if prec != "fp32" else "f32", data="synthetic",
+            scaling="weak", vs_baseline=None, dtype=f"{prec} soft-map forward + backward on tcgen05 (fp32 accumulate, exact fp32 top-k terms)" if prec != "fp32" else "f32", data="synthetic",
             config=dict(workload=f"config 4 training step: GraphDeformLoss_Neural fwd+bwd, N=M={n}, C={C}, alpha={args.alpha}, B={B} pairs/GPU, "
                                  f"stand-in feature head with LG-Net's parameter count, Deformer, Adam",
                         pairs_per_step_per_gpu=B, parallelism=f"data parallel over {world} GPU(s): one flattened NCCL all-reduce of {n_params * 4 / 1e6:.2f} MB per step",
