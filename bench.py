@@ -81,6 +81,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.power_w, self.mem_mhz, self.temp_c = [], [], []
 
     def run(self):
         try:
@@ -91,6 +92,12 @@ class ClockSampler(threading.Thread):
             names = {getattr(pynvml, n): n for n in dir(pynvml) if n.startswith("nvmlClocksThrottleReason") and not n.endswith("All")}
             while not self.stop_flag:
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:                                   # diagnostics for a slow rank: board power, memory clock, temperature
+                    self.power_w.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    self.mem_mhz.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_MEM))
+                    self.temp_c.append(pynvml.nvmlDeviceGetTemperature(h, pynvml.NVML_TEMPERATURE_GPU))
+                except Exception:
+                    pass
                 r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, n in names.items():
                     if bit and (r & bit):
@@ -105,6 +112,11 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz,
                     reasons=sorted(r for r in self.reasons if r not in ("GpuIdle", "None", "ApplicationsClocksSetting")),
                     rejected=bool(bad & self.reasons))
+
+
+def _median(v):
+    v = sorted(v)
+    return v[len(v) // 2] if v else None
 
 
 def physical_gpu_index(local):
@@ -374,11 +386,6 @@ def run_b200(args):
         rank_ms = [round(v / steps, 3) for v in timed_loop.rank_ms]
         sampler.stop_flag = True
         sampler.join(timeout=2)
-        clocks_by_rank = None
-        if dist is not None:                       # diagnostic: median SM clock and throttle reasons of every rank's GPU
-            objs = [None] * world
-            dist.all_gather_object(objs, sampler.summary())
-            clocks_by_rank = [[o.get("sm_mhz"), o.get("reasons")] for o in objs]
 
         # ---- rooflines: the same steps launched eagerly with the library's CUDA-event brackets
         lib.dvm_profile_enable(1)
@@ -386,6 +393,14 @@ def run_b200(args):
         cand_ms, cand_cnt = read_profile(lib, 0)
         fused_ms, fused_cnt = read_profile(lib, 1)
         lib.dvm_profile_enable(0)
+        clocks_by_rank = None
+        if dist is not None:                       # diagnostic: what every rank's GPU did (a slow rank sets the whole-job value)
+            objs = [None] * world
+            mine = dict(sampler.summary(), power_w=_median(sampler.power_w), mem_mhz=_median(sampler.mem_mhz), temp_c=_median(sampler.temp_c),
+                        sweep_ms=round(cand_ms / max(cand_cnt, 1), 4), softmap_ms=round(fused_ms / max(fused_cnt, 1), 4),
+                        gpu=physical_gpu_index(local))
+            dist.all_gather_object(objs, mine)
+            clocks_by_rank = [{k: o.get(k) for k in ("gpu", "sm_mhz", "reasons", "power_w", "mem_mhz", "temp_c", "sweep_ms", "softmap_ms")} for o in objs]
         # the warm-up step of that loop is bracketed too: per-launch averages are what is used below
         res = dict(ms=ms, eager_ms=eager_ms, launches=int(round(launches_per_step * steps)), nring=nring, graph_cold_s=graph_cold_s,
                    clocks=sampler.summary(), rank_ms=rank_ms, clocks_by_rank=clocks_by_rank,

@@ -38,6 +38,15 @@ void prof_end(cudaStream_t st, int ch = 0);     // kernels, channel 1 = the whol
              dvm::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
              return (int)e__; } } while (0)
 
+// Per-device one-time setup (cudaFuncSetAttribute is a per-device property: a process that drives several GPUs must repeat it
+// on each).  `if (once.need()) { ...; once.done(); }`
+struct PerDeviceOnce {
+    unsigned long long mask = 0;                       // bit d = done on device d (races only repeat an idempotent call)
+    static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+    bool need() const { return !((mask >> dev()) & 1ull); }
+    void done() { mask |= 1ull << dev(); }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -264,13 +264,13 @@ extern "C" int dvm_linear_act_fwd(const float* x, long long rows, int K, int x_p
     if ((rc = make_f32_map(&tmW, W, N, K, w_pitch, p.BN))) return rc;
     const size_t smem = (size_t)LIN_NST * 2 * (LIN_BM + p.BN) * LIN_ROW_BYTES + 1024 + 256 + (size_t)p.n_tiles * p.BN * 4;
     if (smem > 227 * 1024) { set_error("dvm_linear_act_fwd: N=%d needs %zu bytes of shared memory", N, smem); return DVM_ERR_UNSUPPORTED; }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
+        attr_done.done();
     }
     const int grid = p.tiles_total < kNumSM ? p.tiles_total : kNumSM;          // persistent: one CTA per SM
     switch (p.BN) {

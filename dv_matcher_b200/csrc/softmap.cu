@@ -8,6 +8,7 @@
 //      (ties -> lower index), emits arg-min, top-k (idx, w, d), row statistics and Pi.V, and certifies
 //      that no discarded column can belong to the top-k given the candidate pass' error bound;
 //   3. rows that fail the certificate are recomputed by the fp32 pass (device-side list, no host sync).
+#include <cooperative_groups.h>
 #include "softmap.cuh"
 
 namespace dvm {
@@ -132,11 +133,11 @@ softmap_cand_simt_kernel(const float* __restrict__ X, const float* __restrict__ 
 int launch_cand_simt(const float* X, const float* Y, int B, int N, int M, int C, float alpha, bool soft,
                      const int* row_list, const int* row_count, int max_rows, CandBuffers cb, cudaStream_t st) {
     const size_t smem = (size_t)(SIMT_BM + SIMT_BN) * (C + 4) * sizeof(float);
-    static bool attr_done[2] = {false, false};
+    static PerDeviceOnce attr_done[2];
     auto kern = soft ? softmap_cand_simt_kernel<true> : softmap_cand_simt_kernel<false>;
-    if (!attr_done[soft]) {
+    if (attr_done[soft].need()) {
         DVM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done[soft] = true;
+        attr_done[soft].done();
     }
     dim3 grid;
     if (row_list) grid = dim3(ceil_div(max_rows, SIMT_BM), 1, 1);
@@ -151,15 +152,16 @@ int launch_cand_simt(const float* X, const float* Y, int B, int N, int M, int C,
 }
 
 // =================================================================================================
-// 1b. exact fp32 pass for a FEW rows (the uncertified rows of the 16-bit pass): one CTA per row, the 256
-//     threads stride over all M columns, so the latency is one column sweep instead of one sweep per
-//     64-row tile.  Two passes over Y: (A) per-thread top-KC -> warp merge -> CTA merge, (B) softmax mass
-//     of the non-candidates relative to the exact row minimum.  Writes partial list 0 of the SIMT buffers.
+// 1b. exact fp32 pass for a FEW rows (the uncertified rows of the 16-bit pass): 32 CTAs per row (see the kernel), each thread
+//     striding over its share of the M columns.  Two passes over Y: (A) per-thread top-KC -> warp merge -> CTA merge -> cluster
+//     merge, (B) softmax mass of the non-candidates relative to the partial list's minimum.  Writes the SIMT partial lists.
 // =================================================================================================
 constexpr int RE_THREADS = 256;
+constexpr int RE_SPLIT = 8;                // CTAs (one cluster) per row; RE_SPLIT * KC = 128 entries in the cluster merge
 
 __device__ __forceinline__ float row_d2(const float* __restrict__ xs, const float* __restrict__ y, int C) {
     float acc = 0.f;
+#pragma unroll 8
     for (int k = 0; k < C; k += 4) {
         const float4 xv = *reinterpret_cast<const float4*>(xs + k);
         const float4 yv = __ldg(reinterpret_cast<const float4*>(y + k));
@@ -172,29 +174,69 @@ __device__ __forceinline__ float row_d2(const float* __restrict__ xs, const floa
     return acc;
 }
 
+// Selection merge of 128 (key, idx) entries held 4 per lane by one warp: KC rounds of lexicographic warp-min; lane 0 hands
+// round s to `emit(s, key, idx)`.
+template <typename Emit>
+__device__ __forceinline__ void re_merge128(float (&ek)[4], int (&ei)[4], Emit emit) {
+    bool taken[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) taken[q] = ei[q] < 0;
+    for (int s = 0; s < KC; ++s) {
+        float bk = INFINITY; int bi = 0x7fffffff; int bq = -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (!taken[q] && kv_less(ek[q], ei[q], bk, bi)) { bk = ek[q]; bi = ei[q]; bq = q; }
+        float wk = bk; int wi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, wk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (kv_less(ok, oi, wk, wi)) { wk = ok; wi = oi; }
+        }
+        if (bq >= 0 && bk == wk && bi == wi) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q == bq) taken[q] = true;
+        }
+        emit(s, wk, wi);
+    }
+}
+
+// cb.P CLUSTERS of RE_SPLIT CTAs per row, one per partial list of the row: the columns are dealt round-robin to the
+// cb.P * RE_SPLIT CTAs, so that the usual case -- a handful of rows, far fewer than SMs -- costs 1/32 of a single-SM column
+// sweep (one row used to take 1.9 ms at M = 50 000 and set the step time of whichever batch contained it).  The per-CTA
+// top-KC lists and masses of a cluster meet in its CTA 0 through distributed shared memory; the finalize pass merges the cb.P
+// partial lists as it does for the SIMT pass.
 template <bool kSoft>
-__global__ void __launch_bounds__(RE_THREADS)
+__global__ void __cluster_dims__(RE_SPLIT, 1, 1) __launch_bounds__(RE_THREADS)
 softmap_rows_exact_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M, int C,
                           const int* __restrict__ row_list, const int* __restrict__ row_count,
                           float a2, float cut_over_alpha, CandBuffers cb) {
+    namespace cg = cooperative_groups;
     __shared__ __align__(16) float xs[256];
     __shared__ float s_key[(RE_THREADS / 32) * KC];
     __shared__ int s_idx[(RE_THREADS / 32) * KC];
     __shared__ float s_red[RE_THREADS / 32];
-    __shared__ float s_wk; __shared__ int s_wi; __shared__ float s_r;
+    __shared__ float s_pk[KC]; __shared__ int s_pi[KC];          // this CTA's partial list (read by CTA 0)
+    __shared__ float s_wk; __shared__ int s_wi; __shared__ float s_r; __shared__ float s_l;
     const int n_rows = *row_count;
-    if (n_rows > ROWS_EXACT_MAX || (int)blockIdx.x >= n_rows) return;
-    const int g = row_list[blockIdx.x];
+    const int slot = blockIdx.x / (RE_SPLIT * cb.P);
+    const int part = (blockIdx.x / RE_SPLIT) % cb.P;             // which partial list of the row this cluster produces
+    if (n_rows > ROWS_EXACT_MAX || slot >= n_rows) return;       // the whole cluster leaves together
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int g = row_list[slot];
     const int b = g / N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int c = tid; c < C; c += RE_THREADS) xs[c] = X[(size_t)g * C + c];
     __syncthreads();
     const float* Yb = Y + (size_t)b * M * C;
+    // the row's columns are dealt round-robin to the cb.P * RE_SPLIT CTAs that work on it
+    const int j0 = (part * RE_SPLIT + crank) * RE_THREADS + tid, jstep = cb.P * RE_SPLIT * RE_THREADS;
 
-    // ---- pass A: per-thread sorted top-KC over columns tid, tid+256, ...
+    // ---- pass A: per-thread sorted top-KC over this CTA's columns
     TopList<KC> list;
     list.init();
-    for (int j = tid; j < M; j += RE_THREADS) {
+    for (int j = j0; j < M; j += jstep) {
         const float d2 = row_d2(xs, Yb + (size_t)j * C, C);
         if (d2 < list.worst()) list.push(d2, j);
     }
@@ -215,66 +257,65 @@ softmap_rows_exact_kernel(const float* __restrict__ X, const float* __restrict__
         if (lane == 0) { s_key[wid * KC + s] = wk; s_idx[wid * KC + s] = wi == 0x7fffffff ? -1 : wi; }
     }
     __syncthreads();
-    // CTA merge by warp 0: 8 x KC = 128 entries, 4 per lane, KC selection rounds
+    // CTA merge by warp 0: 8 warps x KC = 128 entries
     if (wid == 0) {
-        float ek[4]; int ei[4]; bool taken[4];
+        float ek[4]; int ei[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { ek[q] = s_key[lane + 32 * q]; ei[q] = s_idx[lane + 32 * q]; taken[q] = ei[q] < 0; }
-        const size_t base = (size_t)g * cb.P * KC;
+        for (int q = 0; q < 4; ++q) { ek[q] = s_key[lane + 32 * q]; ei[q] = s_idx[lane + 32 * q]; }
+        re_merge128(ek, ei, [&](int s, float wk, int wi) { if (lane == 0) { s_pk[s] = wk; s_pi[s] = wi == 0x7fffffff ? -1 : wi; } });
+    }
+    cluster.sync();
+    // cluster merge by warp 0 of CTA 0: RE_SPLIT x KC = 128 entries, read from the peers' shared memory
+    if (crank == 0 && wid == 0) {
+        float ek[4]; int ei[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = lane + 32 * q;
+            ek[q] = *cluster.map_shared_rank(&s_pk[e % KC], e / KC);
+            ei[q] = *cluster.map_shared_rank(&s_pi[e % KC], e / KC);
+        }
+        const size_t base = ((size_t)g * cb.P + part) * KC;
         float best = INFINITY;
-        for (int s = 0; s < KC; ++s) {
-            float bk = INFINITY; int bi = 0x7fffffff; int bq = -1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (!taken[q] && kv_less(ek[q], ei[q], bk, bi)) { bk = ek[q]; bi = ei[q]; bq = q; }
-            float wk = bk; int wi = bi;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ok = __shfl_xor_sync(0xffffffffu, wk, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-                if (kv_less(ok, oi, wk, wi)) { wk = ok; wi = oi; }
-            }
-            if (bq >= 0 && bk == wk && bi == wi) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) if (q == bq) taken[q] = true;
-            }
+        re_merge128(ek, ei, [&](int s, float wk, int wi) {
             if (s == 0) best = wk;
             if (lane == 0) {
                 cb.key[base + s] = wk;
                 cb.idx[base + s] = wi == 0x7fffffff ? -1 : wi;
                 if (s == KC - 1) { s_wk = wk; s_wi = wi; }
             }
-        }
+        });
         if (lane == 0) s_r = sqrtf(best);
-        // the other partial lists of this row are empty
-        for (int e = KC + lane; e < cb.P * KC; e += 32) { cb.key[base + e] = INFINITY; cb.idx[base + e] = -1; }
     }
-    __syncthreads();
+    cluster.sync();
     // ---- pass B: mass of the non-candidates, relative to the exact row minimum
+    const float r = *cluster.map_shared_rank(&s_r, 0);
     float l = 0.f;
     if (kSoft) {
-        const float wk = s_wk; const int wi = s_wi; const float r = s_r;
+        const float wk = *cluster.map_shared_rank(&s_wk, 0);
+        const int wi = *cluster.map_shared_rank(&s_wi, 0);
         const float te = r + cut_over_alpha;
         const float cut2 = te * te;
-        for (int j = tid; j < M; j += RE_THREADS) {
+        for (int j = j0; j < M; j += jstep) {
             const float d2 = row_d2(xs, Yb + (size_t)j * C, C);
             if (kv_less(wk, wi, d2, j) && d2 < cut2) l += exp2f(-a2 * (sqrtf(d2) - r));
         }
         l = warp_sum(l);
         if (lane == 0) s_red[wid] = l;
         __syncthreads();
-        if (tid == 0) { l = 0.f; for (int w = 0; w < RE_THREADS / 32; ++w) l += s_red[w]; }
+        if (tid == 0) { l = 0.f; for (int w = 0; w < RE_THREADS / 32; ++w) l += s_red[w]; s_l = l; }
     }
-    if (tid == 0) {
-        for (int q = 0; q < cb.P; ++q) {
-            cb.l[(size_t)g * cb.P + q] = q == 0 ? l : 0.f; cb.r[(size_t)g * cb.P + q] = q == 0 ? s_r : INFINITY; cb.t[(size_t)g * cb.P + q] = INFINITY;
-        }
+    cluster.sync();
+    if (crank == 0 && tid == 0) {
+        l = 0.f;
+        if (kSoft) for (int q = 0; q < RE_SPLIT; ++q) l += *cluster.map_shared_rank(&s_l, q);
+        cb.l[(size_t)g * cb.P + part] = l; cb.r[(size_t)g * cb.P + part] = r; cb.t[(size_t)g * cb.P + part] = INFINITY;
     }
+    cluster.sync();                                               // nobody exits while CTA 0 may still read its shared memory
 }
 
 static int launch_rows_exact(const float* X, const float* Y, int N, int M, int C, float alpha, bool soft,
                              const int* row_list, const int* row_count, int max_rows, CandBuffers cb, cudaStream_t st) {
-    const int grid = max_rows < ROWS_EXACT_MAX ? max_rows : ROWS_EXACT_MAX;
+    const int grid = RE_SPLIT * cb.P * (max_rows < ROWS_EXACT_MAX ? max_rows : ROWS_EXACT_MAX);
     const float a2 = alpha * kLog2e;
     const float coa = alpha > 0.f ? kExpCut / alpha : INFINITY;
     if (soft) softmap_rows_exact_kernel<true><<<grid, RE_THREADS, 0, st>>>(X, Y, N, M, C, row_list, row_count, a2, coa, cb);
@@ -809,11 +850,11 @@ static int softmap_fwd_impl(const float* X, const float* Y, const float* V,
         const float a2 = alpha * kLog2e;
         if (nch <= RESC_NCH_MAX) {
             const size_t rsm = ((size_t)RESC_CHUNK * (C + 4) + (size_t)RESC_ROWS * C) * sizeof(float);
-            static bool attr_done = false;
-            if (!attr_done) {
+            static PerDeviceOnce attr_done;
+            if (attr_done.need()) {
                 DVM_CUDA(cudaFuncSetAttribute(rescue_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
                 DVM_CUDA(cudaFuncSetAttribute(rescue_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                attr_done = true;
+                attr_done.done();
             }
             dim3 grid(nch, B);
             if (soft) rescue_scan_kernel<true><<<grid, 256, rsm, st>>>(X, Y, N, M, C, flag_list, st_out, rw.flag_thr, rw.flag_r, a2, nch, rw.cnt, rw.idx, rw.mass);

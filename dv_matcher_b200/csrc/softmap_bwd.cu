@@ -238,11 +238,11 @@ extern "C" int dvm_softmap_bwd(const float* X, const float* Y, int B, int N, int
     softmap_bwd_rowstat_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(top_w, dW, rows, topk, cvec);
     DVM_LAUNCH_CHECK();
     const size_t smem = ((size_t)2 * BW_T * (C + 4) + BW_T * (BW_T + 1) + 3 * BW_T) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         DVM_CUDA(cudaFuncSetAttribute(softmap_bwd_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(softmap_bwd_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done = true;
+        attr_done.done();
     }
     const float a2 = alpha * kLog2e;
     // window: terms below exp(-cut) of the row maximum are dropped (<= M * 1e-14 of the row's gradient mass)

@@ -426,11 +426,11 @@ extern "C" int dvm_softmap_bwd_tc(const float* X, const float* Y, int B, int N, 
     p.xx = w.xx; p.coef = w.coef; p.rmin = row_min; p.coef_max = w.coef_max;
     const size_t unit = (size_t)p.KB * BT_BLK + BT_EXT;
     const size_t smem = (1 + BT_NST) * unit + 2 * 2 * BT_BLK + (3 * 2 * BT_N + 2 * BT_M) * sizeof(float) + 256;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         DVM_CUDA(cudaFuncSetAttribute(softmap_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(softmap_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
+        attr_done.done();
     }
     if (smem > 227 * 1024) { set_error("dvm_softmap_bwd_tc: needs %zu bytes of shared memory", smem); return DVM_ERR_UNSUPPORTED; }
     // owners = X rows, swept = Y columns  -> dX

@@ -703,13 +703,13 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     const bool dense = soft && alpha < TC_DENSE_ALPHA && p.tiles_total >= TC_PRIME_MIN_TILES;
     auto kern = !soft ? softmap_cand_tc_kernel<false, false> : dense ? softmap_cand_tc_kernel<true, false, true> : softmap_cand_tc_kernel<true, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(softmap_cand_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DVM_CUDA(cudaFuncSetAttribute(kprime, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
+        attr_done.done();
     }
     if (smem > 227 * 1024) { set_error("launch_cand_tc: C=%d needs %zu bytes of shared memory", C, smem); return DVM_ERR_UNSUPPORTED; }
     prof_begin(st);

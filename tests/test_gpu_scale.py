@@ -94,6 +94,38 @@ def test_softmap_f16_at_benchmarked_sizes(n, pairs, regime):
     assert torch.equal(hard.argmin, outs[0].argmin)
 
 
+def test_softmap_f16_exact_row_fallback_at_50k():
+    """A batch in which one row survives both the certificate and the rescue scan and takes the exact per-row kernel (a cluster
+    of CTAs per row): every row of the 16-bit path must agree with the fp32 path -- same ten indices, weights within the bound --
+    and the fallback must cost microseconds, not a single-SM sweep of all 50 000 columns."""
+    from dv_matcher_b200 import ops, synthetic
+    d = synthetic.make_batch(2, 50000, 50000, first_pair=28)
+    X = torch.cat([d["feat1"], d["feat2"]]).cuda()
+    Y = torch.cat([d["feat2"], d["feat1"]]).cuda()
+    V = torch.cat([d["xyz2"], d["xyz1"]]).cuda()
+    out = ops.softmap_fwd(X, Y, V, alpha=100.0, prec="f16", want_stats=True)
+    ref = ops.softmap_fwd(X, Y, V, alpha=100.0, prec="fp32")
+    torch.cuda.synchronize()
+    st = out.stats.cpu().tolist()
+    assert st[2] >= 1, f"this batch no longer reaches the exact-row kernel (stats {st}): pick another one"
+    assert torch.equal(out.argmin, ref.argmin) and torch.equal(out.top_idx, ref.top_idx)
+    sig = ref.top_w > 1e-6
+    werr = ((out.top_w - ref.top_w).abs() / ref.top_w.clamp_min(1e-12))[sig].max().item()
+    perr = (out.piv - ref.piv).abs().max().item() / V.abs().max().item()
+    for _ in range(2):
+        ops.softmap_fwd(X, Y, V, alpha=100.0, prec="f16")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(5):
+        ops.softmap_fwd(X, Y, V, alpha=100.0, prec="f16")
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 5
+    _report("softmap_f16_exact_row_fallback", stats=st, w_rel_err_vs_fp32=werr, piv_err_vs_fp32=perr, ms_per_call=ms)
+    assert werr <= F16_W_BOUND and perr <= F16_W_BOUND
+    assert ms < 4.5, ms                     # 4.0 ms without a fallback row; 6.0 ms when one CTA swept the row
+
+
 def test_softmap_f16_200k_one_problem():
     """Config 5's largest size: one 200k x 200k problem (the reference cannot hold its N x M matrix at all)."""
     from dv_matcher_b200 import ops, synthetic
