@@ -157,6 +157,7 @@ int launch_cand_simt(const float* X, const float* Y, int B, int N, int M, int C,
 //     merge, (B) softmax mass of the non-candidates relative to the partial list's minimum.  Writes the SIMT partial lists.
 // =================================================================================================
 constexpr int RE_THREADS = 256;
+constexpr int RE_SLOTS = 32;               // row slots of the launch (x 32 CTAs each)
 constexpr int RE_SPLIT = 8;                // CTAs (one cluster) per row; RE_SPLIT * KC = 128 entries in the cluster merge
 
 __device__ __forceinline__ float row_d2(const float* __restrict__ xs, const float* __restrict__ y, int C) {
@@ -219,14 +220,16 @@ softmap_rows_exact_kernel(const float* __restrict__ X, const float* __restrict__
     __shared__ float s_pk[KC]; __shared__ int s_pi[KC];          // this CTA's partial list (read by CTA 0)
     __shared__ float s_wk; __shared__ int s_wi; __shared__ float s_r; __shared__ float s_l;
     const int n_rows = *row_count;
-    const int slot = blockIdx.x / (RE_SPLIT * cb.P);
     const int part = (blockIdx.x / RE_SPLIT) % cb.P;             // which partial list of the row this cluster produces
-    if (n_rows > ROWS_EXACT_MAX || slot >= n_rows) return;       // the whole cluster leaves together
+    if (n_rows > ROWS_EXACT_MAX) return;
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // the grid holds RE_SLOTS row slots (an empty launch -- the usual case -- must cost nothing); the whole cluster walks the
+    // rows slot, slot + RE_SLOTS, ... together
+    for (int slot = blockIdx.x / (RE_SPLIT * cb.P); slot < n_rows; slot += gridDim.x / (RE_SPLIT * cb.P)) {
     const int g = row_list[slot];
     const int b = g / N;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int c = tid; c < C; c += RE_THREADS) xs[c] = X[(size_t)g * C + c];
     __syncthreads();
     const float* Yb = Y + (size_t)b * M * C;
@@ -310,12 +313,13 @@ softmap_rows_exact_kernel(const float* __restrict__ X, const float* __restrict__
         if (kSoft) for (int q = 0; q < RE_SPLIT; ++q) l += *cluster.map_shared_rank(&s_l, q);
         cb.l[(size_t)g * cb.P + part] = l; cb.r[(size_t)g * cb.P + part] = r; cb.t[(size_t)g * cb.P + part] = INFINITY;
     }
-    cluster.sync();                                               // nobody exits while CTA 0 may still read its shared memory
+    cluster.sync();                                               // nobody exits (or starts the next row) while CTA 0 may still read its shared memory
+    }
 }
 
 static int launch_rows_exact(const float* X, const float* Y, int N, int M, int C, float alpha, bool soft,
                              const int* row_list, const int* row_count, int max_rows, CandBuffers cb, cudaStream_t st) {
-    const int grid = RE_SPLIT * cb.P * (max_rows < ROWS_EXACT_MAX ? max_rows : ROWS_EXACT_MAX);
+    const int grid = RE_SPLIT * cb.P * (max_rows < RE_SLOTS ? max_rows : RE_SLOTS);
     const float a2 = alpha * kLog2e;
     const float coa = alpha > 0.f ? kExpCut / alpha : INFINITY;
     if (soft) softmap_rows_exact_kernel<true><<<grid, RE_THREADS, 0, st>>>(X, Y, N, M, C, row_list, row_count, a2, coa, cb);

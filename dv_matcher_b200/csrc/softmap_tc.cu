@@ -42,6 +42,8 @@ constexpr int TC_CHUNK = 16;               // columns per min-tree
 constexpr int TC_PRIME_STRIDE = 10;        // priming pass: every 10th tile.  Measured at 4 x 50k x 50k (prime + sweep, ms): stride 16: 3.24,
                                            // 12: 3.18, 10: 3.155, 8: 3.15; <= 6: thresholds so tight that rows run out of candidates (slow path)
 constexpr int TC_PRIME_MIN_TILES = 16;      // ... when the sweep has at least this many tiles (M >= 4k): below, the sample is too small
+constexpr int TC_PRIME_FULL_TILES = 96;     // ... and up to this many tiles (M <= 24k) the priming pass is exhaustive (measured, one wave of CTA
+                                            // pairs, prime + sweep us: 20 tiles 176 -> 83, 40: 185 -> 109, 80: 218 -> 176, 200: 321 -> 379)
 constexpr float TC_DENSE_ALPHA = 40.f;      // soft maps with alpha below this run the dense-window instance of the sweep
 
 
@@ -52,6 +54,7 @@ struct TcParams {
     int N, M, KB;                // KB = Cpad / 64
     int tiles_total, tiles_per_split;
     int tile_stride;             // 1 for the sweep; > 1: the priming pass visits every tile_stride-th tile only
+    int prime_rank;              // priming pass: the row threshold is the prime_rank-th smallest chunk minimum it saw (per CTA)
     int multi_split;             // column-split CTAs exchange thresholds through thr_global during the sweep
     float a2, cut_over_alpha;
     uint32_t idesc;
@@ -539,7 +542,7 @@ softmap_cand_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const float2* L2 = L + TC_SUB * LIST_STRIDE;
                     int i0 = 0, i1 = KP, i2 = 0, i3 = KP;
                     float w = INFINITY;
-                    for (int t = 0; t < KP; ++t) {
+                    for (int t = 0; t < p.prime_rank; ++t) {
                         const float a0 = i0 < KP ? L[i0].x : INFINITY, a1 = i1 < 2 * KP ? L[i1].x : INFINITY;
                         const float a2 = i2 < KP ? L2[i2].x : INFINITY, a3 = i3 < 2 * KP ? L2[i3].x : INFINITY;
                         const float m01 = fminf(a0, a1), m23 = fminf(a2, a3);
@@ -700,7 +703,13 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
                         + TC_CONS_WARPS * sizeof(QCtl) + 128;
     // dense-window instance for small alpha (needs the priming pass' reference): crossover measured between alpha = 10
     // (91 -> 300 TFLOP/s at 50k) and alpha = 100 (810 -> 390 when forced)
-    const bool dense = soft && alpha < TC_DENSE_ALPHA && p.tiles_total >= TC_PRIME_MIN_TILES;
+    // Priming: a sample of every 10th tile (threshold ~ rank 80-160 of the row) for long sweeps; for SHORT sweeps the consumers'
+    // start-up (every key below the threshold is queued until the lists fill) costs ~150 us per CTA pair however few tiles
+    // follow, so there the priming pass visits EVERY tile and hands over the 16th smallest chunk minimum -- an exact bound with
+    // at least 16 keys below it, i.e. the lists start full.
+    const bool prime_full = p.tiles_total <= TC_PRIME_FULL_TILES && p.tiles_total >= 2;
+    const bool primed = prime_full || p.tiles_total >= TC_PRIME_MIN_TILES;
+    const bool dense = soft && alpha < TC_DENSE_ALPHA && primed;
     auto kern = !soft ? softmap_cand_tc_kernel<false, false> : dense ? softmap_cand_tc_kernel<true, false, true> : softmap_cand_tc_kernel<true, false>;
     auto kprime = softmap_cand_tc_kernel<false, true>;
     static PerDeviceOnce attr_done;
@@ -713,9 +722,10 @@ int launch_cand_tc(const float* X, const float* Y, int B, int N, int M, int C, f
     }
     if (smem > 227 * 1024) { set_error("launch_cand_tc: C=%d needs %zu bytes of shared memory", C, smem); return DVM_ERR_UNSUPPORTED; }
     prof_begin(st);
-    if (p.tiles_total >= TC_PRIME_MIN_TILES) {       // priming pass over every 10th tile (10 % of the sweep's MMA work)
+    if (primed) {
         TcParams pp = p;
-        pp.tile_stride = TC_PRIME_STRIDE; pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
+        pp.tile_stride = prime_full ? 1 : TC_PRIME_STRIDE; pp.prime_rank = prime_full ? 2 * KP : KP;
+        pp.tiles_per_split = p.tiles_total; pp.multi_split = 0;
         dim3 gridp(2 * ceil_div(N, TC_BM), 1, B);                 // clusters of 2 CTAs along x
         kprime<<<gridp, TC_THREADS, smem, st>>>(tmX, tmXe, tmY, tmYe, pp);
         DVM_LAUNCH_CHECK();
