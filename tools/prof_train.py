@@ -25,3 +25,12 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
+if os.environ.get("CPU_TABLE"):
+    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=60))
+    import time
+    t = time.perf_counter()
+    for _ in range(20): step()
+    t_issue = (time.perf_counter() - t) / 20
+    torch.cuda.synchronize()
+    t_all = (time.perf_counter() - t) / 20
+    print(f"host issue time per step {t_issue * 1e3:.2f} ms ; wall per step {t_all * 1e3:.2f} ms")
