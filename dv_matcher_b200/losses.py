@@ -99,6 +99,10 @@ class _GraphDeformBase(nn.Module):
         self._graph_cache = {}
         self._graph_slot = 0
         self._iden6 = {}
+        # set by training.CapturedTrainStep: graphs and sampled query indices live in STATIC device buffers that are refilled
+        # before every replay of the captured step (nothing inside forward may touch the host then)
+        self.static_graphs = None        # [(nodes_idx float [B,K], BatchedGraph) for verts1, same for verts2]
+        self.static_draws = None         # (int64 [N_dist] for shape 1, same for shape 2)
 
     # -- pieces of the reference API -----------------------------------------------------------------
     def topk_pi(self, A):
@@ -110,6 +114,10 @@ class _GraphDeformBase(nn.Module):
     def deformation_graph_node(self, verts1):
         """Batched graphs of models/loss.py:1325-1337.  Returns (nodes_idx [B,K] float like the reference's
         `num_nodes_all`, BatchedGraph) -- the second item replaces the reference's list of per-cloud objects."""
+        if self.static_graphs is not None:
+            out = self.static_graphs[self._graph_slot % 2]
+            self._graph_slot += 1
+            return out
         key = None
         if self.cache_graphs:
             if self.graph_keys is None:
@@ -138,8 +146,11 @@ class _GraphDeformBase(nn.Module):
         return t
 
     def _dist_loss(self, feat1, feat2, dist1, dist2):
-        numbers1 = random.sample(range(dist1.shape[1]), self.N_dist)      # same host-RNG draw order as :1361-1364
-        numbers2 = random.sample(range(dist2.shape[1]), self.N_dist)
+        if self.static_draws is not None:
+            numbers1, numbers2 = self.static_draws
+        else:
+            numbers1 = random.sample(range(dist1.shape[1]), self.N_dist)      # same host-RNG draw order as :1361-1364
+            numbers2 = random.sample(range(dist2.shape[1]), self.N_dist)
         s1 = dist_loss_term(feat1, dist1, self.N_dist, self.k_dist, numbers1)
         s2 = dist_loss_term(feat2, dist2, self.N_dist, self.k_dist, numbers2)
         return (s1 + s2) * self.w_dist

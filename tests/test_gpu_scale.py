@@ -371,3 +371,59 @@ def test_giant_pair_row_sharding_equals_unsharded():
     _report("giant_pair_sharding", w_rel_max=rel.max().item(), frac_rows_beyond_2e5=loose)
     assert rel.max().item() <= F16_W_BOUND and loose <= 0.01, (rel.max().item(), loose)
     assert torch.allclose(torch.cat([p["verts_t"] for p in parts], 1), vt, rtol=F16_W_BOUND, atol=F16_W_BOUND * v2.abs().max().item())
+
+
+def test_captured_train_step_equals_eager():
+    """training.CapturedTrainStep (forward + backward replayed as one CUDA graph from static buffers) against the eager step on
+    two different batches, twice each: same loss tuple, same gradients, same host-RNG draws."""
+    import gc
+    import random
+    from dv_matcher_b200 import synthetic, training
+    from dv_matcher_b200.deformer import Deformer
+    from dv_matcher_b200.deformation_graph import build_graphs
+    from dv_matcher_b200.losses import GraphDeformLoss_Neural
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    n = 2000
+    head = torch.nn.Linear(128, 128).to(dev)
+    deformer = Deformer(10).to(dev)
+    params = list(head.parameters()) + list(deformer.parameters())
+
+    def mk():
+        return GraphDeformLoss_Neural(k_deform=10, w_dist=0.02, w_map=0.005, k_dist=100, N_dist=200, partial=False, w_deform=0.5,
+                                      w_img=0, w_rank=0, w_self_rec=0.5, w_cd=0.1, w_arap=0.01, save_name="t")
+
+    batches, graphs = [], []
+    for q in range(2):
+        d = {k: v.to(dev) for k, v in synthetic.make_batch(2, n, n, first_pair=2 * q).items()}
+        d["dist1"], d["dist2"] = torch.cdist(d["xyz1"], d["xyz1"]), torch.cdist(d["xyz2"], d["xyz2"])
+        batches.append({k: d[k] for k in ("feat1", "feat2", "dist1", "dist2", "xyz1", "xyz2")})
+        z = torch.zeros(2, dtype=torch.int64, device=dev)
+        graphs.append((build_graphs(d["xyz1"], z), build_graphs(d["xyz2"], z)))
+    crit = mk()
+    eager = []
+    for q in range(2):
+        random.seed(5 + q)
+        for p in params:
+            p.grad = None
+        crit.static_graphs = [(g.nodes_idx.float(), g) for g in graphs[q]]
+        d = batches[q]
+        out = crit(head(d["feat1"]), head(d["feat2"]), d["dist1"], d["dist2"], d["xyz1"], d["xyz2"], 100.0, deformer)
+        out[0].backward()
+        eager.append((torch.stack([o.detach() for o in out]).clone(), torch.cat([p.grad.reshape(-1) for p in params]).clone()))
+    del out, crit
+    gc.collect()                       # no eager autograd graph may stay alive (its AccumulateGrad nodes pin the default stream)
+    step = training.CapturedTrainStep(mk(), lambda a, b: (head(a), head(b)), deformer, params, 100.0)
+    for rep in range(2):
+        for q in range(2):
+            random.seed(5 + q)
+            out = step(batches[q], graphs[q])
+            torch.cuda.synchronize()
+            got = torch.stack(list(out))
+            g = torch.cat([p.grad.reshape(-1) for p in params])
+            le, ge = eager[q]
+            assert torch.allclose(got, le, rtol=1e-5), (got, le)
+            rel = float((g - ge).abs().max() / ge.abs().max())
+            _report("captured_train_step", rep=rep, batch=q, grad_rel_diff=rel, launches_per_step=step.launches_per_step)
+            assert rel <= 1e-4, rel
+    assert step.launches_per_step > 50

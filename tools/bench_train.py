@@ -79,30 +79,53 @@ def run(args):
 
     nring = 4
     ring = [make(q) for q in range(nring)]
+    use_graph = not args.no_cuda_graph
     bucket = [None]
     ev = {k: [] for k in ("fwd", "bwd", "ar", "opt")}
+    captured = None
+    if use_graph:
+        # forward + backward as ONE CUDA graph (dv_matcher_b200.training): batch, deformation graphs and the dist-loss query
+        # indices are refilled into static buffers before every replay; the graphs of the ring's shapes are built once
+        # (what crit.cache_graphs does on the eager path)
+        from dv_matcher_b200 import training
+        from dv_matcher_b200.deformation_graph import build_graphs, draw_fps_start
+        ring_graphs = [tuple(build_graphs(g[k], draw_fps_start(B, n)) for k in ("xyz1", "xyz2")) for g in ring]
+        captured = training.CapturedTrainStep(crit, lambda a, b: (head(a), head(b)), deformer, params, args.alpha)
+        ev = {k: [] for k in ("fwdbwd", "ar", "opt")}
+
+    def batch_of(g):
+        return {k: g[k] for k in ("feat1", "feat2", "dist1", "dist2", "xyz1", "xyz2")}
 
     def step(i, data=None, record=False):
         g = data or ring[i % nring]
-        crit.graph_keys = (("s1", rank if data is None else -1, i % nring), ("s2", rank if data is None else -1, i % nring))
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
         if record:
             marks[0].record()
-        f1, f2 = head(g["feat1"]), head(g["feat2"])
-        out = crit(f1, f2, g["dist1"], g["dist2"], g["xyz1"], g["xyz2"], args.alpha, deformer)
-        if record:
-            marks[1].record()
-        opt.zero_grad(set_to_none=False)
-        out[0].backward()
-        if record:
-            marks[2].record()
+        if captured is not None:
+            graphs = same_graphs if data is not None else ring_graphs[i % nring]
+            out = captured(batch_of(g), graphs)
+            if record:
+                marks[2].record()
+        else:
+            crit.graph_keys = (("s1", rank if data is None else -1, i % nring), ("s2", rank if data is None else -1, i % nring))
+            f1, f2 = head(g["feat1"]), head(g["feat2"])
+            out = crit(f1, f2, g["dist1"], g["dist2"], g["xyz1"], g["xyz2"], args.alpha, deformer)
+            if record:
+                marks[1].record()
+            opt.zero_grad(set_to_none=False)
+            out[0].backward()
+            if record:
+                marks[2].record()
         bucket[0] = dd.allreduce_gradients(params, world=world, bucket=bucket[0])
         if record:
             marks[3].record()
         opt.step()
         if record:
             marks[4].record()
-            ev["fwd"].append((marks[0], marks[1])); ev["bwd"].append((marks[1], marks[2]))
+            if captured is not None:
+                ev["fwdbwd"].append((marks[0], marks[2]))
+            else:
+                ev["fwd"].append((marks[0], marks[1])); ev["bwd"].append((marks[1], marks[2]))
             ev["ar"].append((marks[2], marks[3])); ev["opt"].append((marks[3], marks[4]))
         return out
 
@@ -111,18 +134,24 @@ def run(args):
     torch.manual_seed(1)
     import random
     random.seed(1)
-    opt.zero_grad(set_to_none=False)
-    f1, f2 = head(same["feat1"]), head(same["feat2"])
-    crit.graph_keys = ("eq1", "eq2")
-    out = crit(f1, f2, same["dist1"], same["dist2"], same["xyz1"], same["xyz2"], args.alpha, deformer)
-    out[0].backward()
+    if captured is not None:
+        same_graphs = tuple(build_graphs(same[k], torch.zeros(B, dtype=torch.int64, device=device)) for k in ("xyz1", "xyz2"))
+        captured(batch_of(same), same_graphs)
+    else:
+        opt.zero_grad(set_to_none=False)
+        f1, f2 = head(same["feat1"]), head(same["feat2"])
+        crit.graph_keys = ("eq1", "eq2")
+        out = crit(f1, f2, same["dist1"], same["dist2"], same["xyz1"], same["xyz2"], args.alpha, deformer)
+        out[0].backward()
+        del out, f1, f2
     local = torch.cat([p.grad.reshape(-1) for p in params]).clone()
     dd.allreduce_gradients(params, world=world)
     after = torch.cat([p.grad.reshape(-1) for p in params])
     grad_eq = float((after - local).abs().max() / local.abs().max().clamp_min(1e-30))
     # run-to-run differences of the 16-bit softmax mass (queue order) reach the gradients at ~1e-6; ranks see the same data
     assert grad_eq <= 1e-3, f"all-reduced gradient differs from the local one by {grad_eq}"
-    opt.zero_grad(set_to_none=False)
+    if captured is None:
+        opt.zero_grad(set_to_none=False)
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -140,6 +169,8 @@ def run(args):
     e1.record()
     torch.cuda.synchronize(device)
     launches = lib.dvm_launch_count() - l0
+    if captured is not None:
+        launches += captured.launches_per_step * args.steps
     sampler.stop_flag = True
     sampler.join(timeout=2)
     ms = e0.elapsed_time(e1)
@@ -162,8 +193,10 @@ def run(args):
             config=dict(workload=f"config 4 training step: GraphDeformLoss_Neural fwd+bwd, N=M={n}, C={C}, alpha={args.alpha}, B={B} pairs/GPU, "
                                  f"stand-in feature head with LG-Net's parameter count, Deformer, Adam",
                         pairs_per_step_per_gpu=B, parallelism=f"data parallel over {world} GPU(s): one flattened NCCL all-reduce of {n_params * 4 / 1e6:.2f} MB per step",
-                        graphs="warm (cached per shape)", prec=prec),
-            phases_ms=dict(forward=phases["fwd"], backward=phases["bwd"], allreduce=phases["ar"], optimizer=phases["opt"]),
+                        graphs="warm (cached per shape)", prec=prec,
+                        launch="forward + backward replayed as one CUDA graph (static buffers refilled per step); all-reduce and Adam eager" if captured is not None else "eager"),
+            phases_ms=(dict(forward_backward_one_cuda_graph=phases["fwdbwd"], allreduce=phases["ar"], optimizer=phases["opt"]) if captured is not None
+                       else dict(forward=phases["fwd"], backward=phases["bwd"], allreduce=phases["ar"], optimizer=phases["opt"])),
             allreduce=dict(bytes=n_params * 4, ms=phases["ar"], backend="nccl" if world > 1 else "none (1 GPU)",
                            gradient_equality_rel_err=grad_eq),
             gpu_launches=int(launches), clocks=sampler.summary(),
