@@ -460,7 +460,8 @@ extern "C" int dvm_gather_conv_bwd(const float* feat, const int64_t* idx, const 
 extern "C" int dvm_sparse_transfer_fwd(const int32_t* idx, const float* w, const float* Y,
                                        int B, int N, int M, int K, int D, float* out, void* stream) {
     DVM_CHECK_ARG(idx && w && Y && out, "dvm_sparse_transfer_fwd: null pointer");
-    DVM_CHECK_ARG(B > 0 && N > 0 && M > 0 && D > 0 && K > 0 && K <= DVM_KNN_MAX, "dvm_sparse_transfer_fwd: bad sizes");
+    // the wide kernel keeps the K (index, weight) pairs of a row in registers (K <= DVM_KNN_MAX); the narrow one (D <= 3) loops over K
+    DVM_CHECK_ARG(B > 0 && N > 0 && M > 0 && D > 0 && K > 0 && (K <= DVM_KNN_MAX || (D <= 3 && K <= 1024)), "dvm_sparse_transfer_fwd: bad sizes");
     const int rows = B * N;
     cudaStream_t st = (cudaStream_t)stream;
     if (D == 3)      sparse_transfer_fwd_narrow_kernel<3><<<ceil_div(rows, 256), 256, 0, st>>>(idx, w, Y, rows, N, M, K, out);

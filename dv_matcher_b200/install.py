@@ -10,7 +10,7 @@ this package does not implement; `uninstall()` restores the originals.
 import importlib
 import sys
 
-from . import deformation_graph, deformer, geometry, losses, maps
+from . import deformation_graph, deformer, geometry, losses, maps, secondary
 
 _saved = []
 
@@ -29,6 +29,9 @@ _SCRIPT_NAMES = dict(
     rotation_6d_to_matrix=geometry.rotation_6d_to_matrix, deformation_graph_node=deformation_graph.deformation_graph_node_list,
     DeformationGraph_geod=deformation_graph.DeformationGraph_geod, Deformer=deformer.Deformer,
     GraphDeformLoss_Neural=losses.GraphDeformLoss_Neural, GraphDeformLoss_Neural_Partial=losses.GraphDeformLoss_Neural_Partial,
+    # secondary (cosine / top-40) API of test_partial.py:73-144
+    forward_source_target=secondary.forward_source_target, forward_shape=secondary.forward_shape,
+    cross_construct=secondary.cross_construct, reconstruction=secondary.reconstruction,
 )
 _TABLE = {
     "models.loss": _LOSS_NAMES,

@@ -404,12 +404,16 @@ def knn_feature_large(a, b, k):
     npad = (N + 3) // 4 * 4
     out = torch.empty(B, S, k, dtype=torch.int64, device=a.device)
     bias = (-0.5) * (b * b).sum(-1)                                    # [B,N]
+    lib = _lib.load()
+    rows_max = max(128, (256 << 20) // (4 * npad))                     # the score matrix only exists as row chunks of <= 256 MB
+    sc = torch.empty(min(S, rows_max), npad, dtype=torch.float32, device=a.device)
     for i in range(B):
-        sc = torch.empty(S, npad, dtype=torch.float32, device=a.device)
-        lib = _lib.load()
-        check(lib.dvm_linear_act_fwd(a[i].data_ptr(), S, C, C, b[i].data_ptr(), C, ptr(bias[i].contiguous()), N, 0, ptr(sc), npad, stream_ptr()),
-              "dvm_linear_act_fwd")
-        out[i] = topk_select(sc, k, n_valid=N)
+        bi = bias[i].contiguous()
+        for r0 in range(0, S, rows_max):
+            r = min(rows_max, S - r0)
+            check(lib.dvm_linear_act_fwd(a[i, r0:r0 + r].data_ptr(), r, C, C, b[i].data_ptr(), C, ptr(bi), N, 0, ptr(sc), npad, stream_ptr()),
+                  "dvm_linear_act_fwd")
+            out[i, r0:r0 + r] = topk_select(sc[:r], k, n_valid=N)
     return out
 
 

@@ -100,7 +100,8 @@ int dvm_softmap_bwd_tc(const float* X, const float* Y, int B, int N, int M, int 
 
 /* 10-sparse transfers Pi @ Y for any row width D: torch.matmul(Pi_12, feat2) models/model.py:471,
  * einsum('bij,bjkm->bikm') models/loss.py:1237 (with Y viewed as [B,M,k*m]).
- * out[b,i,:] = sum_k w[b,i,k] * Y[b, idx[b,i,k], :].   bwd: dW = <dOut, Y[idx]>, dY += w * dOut. */
+ * out[b,i,:] = sum_k w[b,i,k] * Y[b, idx[b,i,k], :].   bwd: dW = <dOut, Y[idx]>, dY += w * dOut.
+ * K <= DVM_KNN_MAX; the forward also takes K <= 1024 when D <= 3 (the top-40 reconstructions of test_partial.py:73-96). */
 int dvm_sparse_transfer_fwd(const int32_t* idx, const float* w, const float* Y,
                             int B, int N, int M, int K, int D, float* out, void* stream);
 int dvm_sparse_transfer_bwd(const int32_t* idx, const float* w, const float* Y, const float* dOut,

@@ -10,6 +10,13 @@ from oracle import geometry as og
 pytestmark = pytest.mark.gpu
 
 
+def _report(name, **kv):
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.jsonl", "a") as f:
+        f.write(json.dumps(dict(test=name, **kv)) + "\n")
+
+
 def test_topk_select_matches_torch_topk_including_ties():
     from dv_matcher_b200 import ops
     gen = torch.Generator().manual_seed(5)
@@ -127,3 +134,37 @@ def test_dist_loss_term_matches_reference_formula():
     g, r = fg.grad.cpu().double(), fd.grad
     cos = float((g * r).sum() / (g.norm() * r.norm()))
     assert cos >= 0.9999 and abs(float(g.norm() / r.norm()) - 1) <= 1e-3, (cos, float(g.norm() / r.norm()))
+
+
+def test_secondary_api_matches_reference_golden():
+    """SURVEY 8a row A11 (cosine similarity -> top-40 along rows and columns -> softmax -> reconstruction; test_partial.py:73-144):
+    the native path (tensor-core scores + radix selection + exact pair similarities + sparse transfer) against the outputs of the
+    unmodified reference.  A row whose 40th and 41st similarities are closer than the 3xTF32 score noise may select the other
+    neighbour (weight ~1/40): such rows are found with the fp64 oracle and excluded (none expected on this fixture)."""
+    import os
+    import numpy as np
+    from dv_matcher_b200 import secondary
+    from oracle import secondary as osec
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_secondary.npz"))
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    g = {k: v.cuda() for k, v in t.items()}
+    src, tgt = secondary.forward_source_target(g["feat_source"], g["feat_target"], g["vert_source"], g["vert_target"])
+    own = secondary.forward_shape(g["feat_source"], g["vert_source"])
+    cross = secondary.cross_construct(g["feat_source"], g["feat_target"], g["vert_target"], 10)
+
+    def fragile(a, b, k):            # rows whose k-th / (k+1)-th similarity gap is below 1e-5
+        P = osec.cosine_similarity_matrix(a.double(), b.double())
+        v = P.topk(k + 1, dim=2)[0]
+        return (v[:, :, k - 1] - v[:, :, k]) < 1e-5
+
+    checks = (("source_cross_recon", src, fragile(t["feat_target"], t["feat_source"], 40)),
+              ("target_cross_recon", tgt, fragile(t["feat_source"], t["feat_target"], 40)),
+              ("self_recon", own, fragile(t["feat_source"], t["feat_source"], 41)),
+              ("cross_construct", cross, torch.zeros(t["cross_construct"].shape[:2], dtype=torch.bool)))
+    for name, got, bad in checks:
+        ref = t[name]
+        err = (got.cpu() - ref).abs().amax(-1)
+        assert bad.float().mean().item() <= 0.01, (name, bad.sum().item())
+        e = err[~bad].max().item() / ref.abs().max().item()
+        _report("secondary_api", which=name, rel_err=e, fragile_rows=int(bad.sum()))
+        assert e <= 1e-4, (name, e)

@@ -159,3 +159,16 @@ def test_chamfer_restatement_properties():
     da, db = og.chamfer_3d_backward(a, b, i1, i2, g1, g2)
     np.testing.assert_allclose(da.numpy(), a2.grad.numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(db.numpy(), b2.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_secondary_api_matches_reference():
+    """oracle/secondary.py against outputs of the unmodified reference (test_partial.py:73-144,
+    tests/golden/make_golden_secondary.py)."""
+    import os
+    from oracle import secondary as osec
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_secondary.npz"))
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    src, tgt = osec.forward_source_target(t["feat_source"], t["feat_target"], t["vert_source"], t["vert_target"])
+    assert torch.equal(src, t["source_cross_recon"]) and torch.equal(tgt, t["target_cross_recon"])
+    assert torch.equal(osec.forward_shape(t["feat_source"], t["vert_source"]), t["self_recon"])
+    assert torch.equal(osec.cross_construct(t["feat_source"], t["feat_target"], t["vert_target"], 10), t["cross_construct"])
