@@ -35,7 +35,9 @@ _SCRIPT_NAMES = dict(
 )
 _TABLE = {
     "models.loss": _LOSS_NAMES,
-    "models.model": dict(Deformer=deformer.Deformer),
+    # LG-Net itself stays the reference's torch code, but its seven N x N k-NN calls per forward (knn_new, k = 40,
+    # models/model.py:267-278) and their gathers (index_points, :255-265) are the same operators as the loss's
+    "models.model": dict(Deformer=deformer.Deformer, knn_new=geometry.knn, index_points=geometry.index_points),
     "lib.deformation_graph_point": dict(DeformationGraph_geod=deformation_graph.DeformationGraph_geod,
                                         farthest_point_sample=deformation_graph.farthest_point_sample),
     "lib.deformation_graph": dict(DeformationGraph=deformation_graph.DeformationGraph),

@@ -168,3 +168,20 @@ def test_secondary_api_matches_reference_golden():
         e = err[~bad].max().item() / ref.abs().max().item()
         _report("secondary_api", which=name, rel_err=e, fragile_rows=int(bad.sum()))
         assert e <= 1e-4, (name, e)
+
+
+def test_lgnet_knn_new_k40():
+    """LG-Net's neighbourhood search (`knn_new(pcd, pcd, 40)`, models/model.py:267-278, seven calls per forward) is
+    `geometry.knn`: tensor-core scores + radix selection against the reference's dense formula at its real size."""
+    from dv_matcher_b200 import geometry
+    gen = torch.Generator().manual_seed(11)
+    for n, c in ((4995, 128), (2048, 64)):
+        x = torch.randn(2, n, c, generator=gen)
+        idx = geometry.knn(x.cuda(), x.cuda(), 40).cpu()
+        xd = x.double()
+        pd = -(xd ** 2).sum(-1, keepdim=True) + 2 * xd @ xd.transpose(1, 2) - (xd ** 2).sum(-1)[:, None, :]      # the reference's score, fp64
+        v, ref = pd.topk(41, dim=-1)
+        assert torch.equal(idx[:, :, 0], torch.arange(n).expand(2, n))           # the point itself comes first
+        safe = (v[:, :, 39] - v[:, :, 40]) > 1e-5 * v[:, :, 40].abs()            # rows whose 40th / 41st neighbours are not a near-tie
+        same = (idx.sort(-1).values == ref[:, :, :40].sort(-1).values).all(-1)
+        assert safe.float().mean() > 0.95 and bool(same[safe].all()), (n, c, float(safe.float().mean()), int((~same & safe).sum()))
