@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-hbm", action="store_true", help="skip the memory-bound kernel microbench (roofline_hbm)")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="compute streams the ring's batches are spread over (CUDA-graph mode)")
     return ap.parse_args()
 
 
@@ -64,7 +65,9 @@ def bench_config(args, world):
                 pairs_per_step_per_gpu=args.pairs, parallelism=f"pairs sharded over {world} GPU(s), no data-path collective",
                 l2_policy="inputs rotate through >= 2 distinct batches (> 126 MB L2 in total)",
                 graphs="warm (built once per shape, outside the timed region)", prec=args.prec,
-                launch="eager launches" if args.no_cuda_graph else "the warm step is one CUDA-graph launch per batch")
+                launch="eager launches" if args.no_cuda_graph else
+                       ("the warm step is one CUDA-graph launch per batch" + (f"; consecutive batches alternate over {args.streams} compute streams "
+                        "(the tail of one step overlaps the sweep of the next)" if args.streams > 1 else "")))
 
 
 def measured_peaks():
@@ -337,6 +340,7 @@ def run_b200(args):
     def bench_size(npts, nb, steps, warmup, with_e2e):
         bytes_per_batch = nb * 2 * npts * (C + 3) * 4
         nring = max(2, min(8, int(130e6 * 1.5 / bytes_per_batch) + 1))      # ring of inputs > 126 MB L2
+        nring = max(nring, 4 if with_e2e else min(args.streams, 4))        # one batch per engine slot (4) / compute stream
         ring = make_ring(npts, nb, nring)
         t0 = time.perf_counter()
         graphs = [build_graphs(torch.cat([d["xyz1"], d["xyz2"]]), torch.arange(2 * nb) % npts) for _, d in ring]
@@ -350,12 +354,16 @@ def run_b200(args):
                                              alpha=args.alpha, prec=args.prec)
 
         # ---- warm-up (also: every lazy one-time initialisation happens here, before any capture)
-        side = torch.cuda.Stream(device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):                  # the capture stream: warm its workspaces with the eager step
-            for i in range(max(warmup, nring)):
-                eager_step(i)
-        torch.cuda.current_stream(device).wait_stream(side)
+        # `--streams 2`: the two input batches of the ring live on two streams (own workspaces, own graph pools), so the
+        # latency-bound tail of one step (k-NN, finalize, decoder MLP, transfers) overlaps the tensor-bound sweep of the next
+        nstreams = max(1, min(args.streams, nring)) if use_graph else 1
+        sides = [torch.cuda.Stream(device) for _ in range(nstreams)]
+        for sd in sides:
+            sd.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(sd):                # a capture stream: warm its workspaces with the eager step
+                for i in range(max(warmup, nring)):
+                    eager_step(i)
+            torch.cuda.current_stream(device).wait_stream(sd)
         for i in range(warmup):
             eager_step(i)
         torch.cuda.synchronize(device)
@@ -364,16 +372,22 @@ def run_b200(args):
         cgs, keep = None, []
         if use_graph:
             _lib.workspace.keep_retired = True
-            pool = torch.cuda.graph_pool_handle()
+            pools = [torch.cuda.graph_pool_handle() for _ in range(nstreams)]
             cgs = []
             for q in range(nring):
                 cg = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(cg, pool=pool, stream=side):
+                with torch.cuda.graph(cg, pool=pools[q % nstreams], stream=sides[q % nstreams]):
                     keep.append(eager_step(q))
                 cgs.append(cg)
 
-            def step(i):
-                cgs[i % nring].replay()
+            if nstreams == 1:
+                def step(i):
+                    cgs[i % nring].replay()
+            else:
+                def step(i):
+                    q = i % nring
+                    with torch.cuda.stream(sides[q % nstreams]):
+                        cgs[q].replay()
         else:
             step = eager_step
         l0 = lib.dvm_launch_count()
@@ -423,15 +437,15 @@ def run_b200(args):
             def estep(i):
                 h, _ = ring[i % nring]
                 pending.append(eng.submit(h["feat1"], h["feat2"], h["xyz1"], h["xyz2"], graph_key=i % nring))
-                if len(pending) == 2:                 # two steps in flight: H2D(i+1) and D2H(i-1) overlap the kernels of step i
+                if len(pending) == 4:                 # four steps in flight (one per engine slot): copies of i+3 / i-1 under the kernels of i .. i+2
                     eng.result(pending.pop(0))
 
             def drain():
                 while pending:
                     eng.result(pending.pop(0))
 
-            e2e_steps = max(4, steps // 2)
-            ems = timed_loop(estep, e2e_steps, max(4, min(warmup, 6)), dist, device, finish=drain)
+            e2e_steps = max(4, steps)                 # the pipeline's fill and drain (one step latency) are inside the timed region
+            ems = timed_loop(estep, e2e_steps, max(9, warmup), dist, device, finish=drain)      # every slot (4) is used twice before timing: eager, then captured
             h0 = ring[0][0]
             res["e2e"] = dict(ms=ems, steps=e2e_steps, h2d=eng.h2d_bytes(h0["feat1"], h0["feat2"], h0["xyz1"], h0["xyz2"]), d2h=eng.d2h_bytes(),
                               launch_mode=eng.launch_mode)
