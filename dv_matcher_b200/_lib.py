@@ -62,6 +62,7 @@ SIGNATURES = {
     "dvm_pair_dist_bwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p, c_void_p]),
     "dvm_gather_rows_fwd": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
     "dvm_gather_rows_bwd": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "dvm_softmax_rows_transposed": (c_int, [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "dvm_linear_act_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

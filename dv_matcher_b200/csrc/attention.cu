@@ -1,0 +1,85 @@
+// Row softmax of a score chunk, written TRANSPOSED (LG-Net's SA_Layer global attention,
+// models/model.py:113-119: energy = x_q x_k; attention = softmax(energy, -1); attention /= 1e-9 + attention.sum(1); x_r = x_v attention).
+//
+// The N x N attention matrix never exists: dv_matcher_b200/lgnet.py walks row chunks.  For a chunk of `rows` query rows
+//   E  [rows][N]  = Q_chunk K^T                        (dvm_linear_act_fwd: tcgen05, 3xTF32, fp32-equivalent)
+//   Pt [N][rows]  = softmax over each row of E, transposed                                    (this kernel)
+//   U  [N][C+1]  += Pt [x_v_chunk | 1]^T                (dvm_linear_act_fwd again: the appended row of ones makes the column sums
+//                                                        of the attention matrix fall out of the same GEMM, deterministically)
+// and x_r[c][j] = U[j][c] / (1e-9 + U[j][C]).  The transposed store is what lets the second GEMM read P with the contraction
+// index (the chunk's rows) contiguous, i.e. K-major like every other operand of that kernel.
+//
+// Two launches: (1) one warp per row reduces (max, sum of exp) with coalesced reads; (2) a 2-D grid of (32 rows x 256 columns)
+// blocks: every warp loads 4 rows x 32 columns, the exponentials go through a padded shared-memory tile and leave as 128-byte row
+// segments of Pt.  E is read three times (the last two from L2), Pt written once.
+#include "common.cuh"
+
+namespace dvm {
+
+constexpr int SM_ROWS = 32;
+constexpr int SM_COLS = 256;
+constexpr int SM_THREADS = 256;
+
+__global__ void __launch_bounds__(256)
+softmax_row_stats_kernel(const float* __restrict__ E, int rows, int N, long long pitch, float* __restrict__ stats /* [rows][2] */) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float* e = E + (size_t)r * pitch;
+    float m = -INFINITY, z = 0.f;                                       // exact max, then sum of exp(e - max): torch.softmax's form
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, __ldg(e + j));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int j = lane; j < N; j += 32) z += expf(__ldg(e + j) - m);
+    z = warp_sum(z);
+    if (lane == 0) { stats[2 * r] = m; stats[2 * r + 1] = z > 0.f ? 1.f / z : 0.f; }
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+softmax_rows_transposed_kernel(const float* __restrict__ E, int rows, int N, long long pitch, const float* __restrict__ stats,
+                               float* __restrict__ Pt, long long pt_pitch) {
+    __shared__ float s_m[SM_ROWS], s_iz[SM_ROWS];
+    __shared__ float tile[SM_ROWS][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * SM_ROWS;
+    const int c_lo = blockIdx.y * SM_COLS, c_hi = min(N, c_lo + SM_COLS);
+    if (threadIdx.x < SM_ROWS) {
+        const int r = r0 + threadIdx.x;
+        s_m[threadIdx.x] = r < rows ? stats[2 * r] : 0.f;
+        s_iz[threadIdx.x] = r < rows ? stats[2 * r + 1] : 0.f;
+    }
+    __syncthreads();
+    for (int j0 = c_lo; j0 < c_hi; j0 += 32) {
+#pragma unroll
+        for (int q = 0; q < SM_ROWS / 8; ++q) {
+            const int rl = wid * (SM_ROWS / 8) + q, r = r0 + rl, j = j0 + lane;
+            float p = 0.f;
+            if (r < rows && j < c_hi) p = expf(__ldg(E + (size_t)r * pitch + j) - s_m[rl]) * s_iz[rl];
+            tile[rl][lane] = p;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jl = wid * 4 + q, j = j0 + jl;          // warp w writes columns 4w .. 4w+3 of the tile as rows of Pt
+            if (j < c_hi && r0 + lane < rows) Pt[(size_t)j * pt_pitch + r0 + lane] = tile[lane][jl];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace dvm
+
+using namespace dvm;
+
+extern "C" int dvm_softmax_rows_transposed(const float* E, int rows, int N, long long pitch, float* Pt, long long pt_pitch,
+                                           float* stats, void* stream) {
+    DVM_CHECK_ARG(E && Pt && stats, "dvm_softmax_rows_transposed: null pointer");
+    DVM_CHECK_ARG(rows > 0 && N > 0 && pitch >= N && pt_pitch >= rows, "dvm_softmax_rows_transposed: bad sizes");
+    DVM_CHECK_ARG(ceil_div(N, SM_COLS) <= 65535, "dvm_softmax_rows_transposed: N too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    softmax_row_stats_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(E, rows, N, pitch, stats);
+    DVM_LAUNCH_CHECK();
+    softmax_rows_transposed_kernel<<<dim3(ceil_div(rows, SM_ROWS), ceil_div(N, SM_COLS)), SM_THREADS, 0, st>>>(E, rows, N, pitch, stats, Pt, pt_pitch);
+    DVM_LAUNCH_CHECK();
+    return 0;
+}

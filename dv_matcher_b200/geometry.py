@@ -34,7 +34,7 @@ def knn(a, b, k, chunk=4096):
     stock matmul and selected by the same kernel."""
     if k <= 10 and a.shape[-1] % 4 == 0:
         return ops.softmap_fwd(a, b, None, topk=k, soft=False, prec="fp32").top_idx.long()
-    if a.is_cuda and a.shape[-1] % 4 == 0 and k <= 1024 and b.shape[1] <= 32768:
+    if a.is_cuda and a.shape[-1] % 4 == 0 and k <= 1024:
         return ops.knn_feature_large(a.detach(), b.detach(), k)
     bb = torch.sum(b ** 2, dim=2, keepdim=True).transpose(2, 1)
     out = []

@@ -10,7 +10,7 @@ this package does not implement; `uninstall()` restores the originals.
 import importlib
 import sys
 
-from . import deformation_graph, deformer, geometry, losses, maps, secondary
+from . import deformation_graph, deformer, geometry, lgnet, losses, maps, secondary
 
 _saved = []
 
@@ -71,6 +71,8 @@ def install(import_missing=True, verbose=False):
         if mod is None or mod.__name__.startswith("dv_matcher_b200"):
             continue
         c = _patch(mod, names)
+        if modname == "models.model" and hasattr(mod, "SA_Layer"):        # LG-Net's global attention without the N x N matrix
+            c += _patch(mod.SA_Layer, dict(forward=lgnet.sa_layer_forward))
         if c:
             done[modname] = c
     if verbose:

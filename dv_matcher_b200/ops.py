@@ -396,6 +396,25 @@ def topk_select(scores, k, n_valid=None):
     return idx
 
 
+LINEAR_MAX_OUT = 8192          # dvm_linear_act_fwd stages its bias row in shared memory: wider outputs go in column blocks
+
+
+def linear_into(x, w, bias, out):
+    """out[:, :N] = x @ w.T (+ bias) with dvm_linear_act_fwd, any N: column blocks of LINEAR_MAX_OUT written straight into `out`
+    ([rows, pitch >= N] float32, pitch a multiple of 4).  x [rows,K], w [N,K] float32 with row pitches that are multiples of 4."""
+    lib = _lib.load()
+    rows, K = x.shape
+    N = w.shape[0]
+    if out.stride(0) % 4 or out.stride(1) != 1 or out.data_ptr() % 16 or x.stride(0) % 4 or w.stride(0) % 4 or x.stride(1) != 1 or w.stride(1) != 1:
+        raise RuntimeError("linear_into: row pitches must be multiples of 4 floats, unit column stride, 16-byte aligned")
+    for c0 in range(0, N, LINEAR_MAX_OUT):
+        nc = min(LINEAR_MAX_OUT, N - c0)
+        check(lib.dvm_linear_act_fwd(x.data_ptr(), rows, K, x.stride(0), w.data_ptr() + 4 * c0 * w.stride(0), w.stride(0),
+                                     (bias.data_ptr() + 4 * c0) if bias is not None else None, nc, 0,
+                                     out.data_ptr() + 4 * c0, out.stride(0), stream_ptr()), "dvm_linear_act_fwd")
+    return out
+
+
 def knn_feature_large(a, b, k):
     """knn(a, b, k) of models/loss.py:451-462 for k > 10: scores 2 a.b - |b|^2 on tcgen05 (3xTF32), radix selection of the k best."""
     a, b = f32c(a), f32c(b)
@@ -403,16 +422,13 @@ def knn_feature_large(a, b, k):
     N = b.shape[1]
     npad = (N + 3) // 4 * 4
     out = torch.empty(B, S, k, dtype=torch.int64, device=a.device)
-    bias = (-0.5) * (b * b).sum(-1)                                    # [B,N]
-    lib = _lib.load()
+    bias = ((-0.5) * (b * b).sum(-1)).contiguous()                     # [B,N]
     rows_max = max(128, (256 << 20) // (4 * npad))                     # the score matrix only exists as row chunks of <= 256 MB
     sc = torch.empty(min(S, rows_max), npad, dtype=torch.float32, device=a.device)
     for i in range(B):
-        bi = bias[i].contiguous()
         for r0 in range(0, S, rows_max):
             r = min(rows_max, S - r0)
-            check(lib.dvm_linear_act_fwd(a[i, r0:r0 + r].data_ptr(), r, C, C, b[i].data_ptr(), C, ptr(bi), N, 0, ptr(sc), npad, stream_ptr()),
-                  "dvm_linear_act_fwd")
+            linear_into(a[i, r0:r0 + r], b[i], bias[i], sc[:r])
             out[i, r0:r0 + r] = topk_select(sc[:r], k, n_valid=N)
     return out
 

@@ -228,6 +228,11 @@ int dvm_pair_dist_bwd(const float* feat, const int64_t* qidx, const int64_t* nbr
 int dvm_gather_rows_fwd(const float* pts, const int64_t* idx, int B, int N, int R, int C, float* out, void* stream);
 int dvm_gather_rows_bwd(const float* d_out, const int64_t* idx, int B, int N, int R, int C, float* d_pts, void* stream);
 
+/* Row softmax of a score chunk E[rows][pitch] (N valid columns), written transposed: Pt[j * pt_pitch + i] = softmax_i(E[i, :])[j].
+ * Middle step of LG-Net's SA_Layer attention without the N x N matrix (models/model.py:113-119; dv_matcher_b200/lgnet.py):
+ * scores and the weighted sum on either side are dvm_linear_act_fwd GEMMs.  stats: scratch of 2 * rows floats (row max, 1 / row sum). */
+int dvm_softmax_rows_transposed(const float* E, int rows, int N, long long pitch, float* Pt, long long pt_pitch, float* stats, void* stream);
+
 /* One layer of the Deformer's decoder MLP (models/model.py:433-452: nn.Linear + nn.ELU; called at :476-477):
  *   out[r, n] = act( sum_k x[r,k] W[n,k] + bias[n] ),  x[rows][x_pitch] (K used), W[N][w_pitch] (nn.Linear layout),
  *   act 0 = identity, 1 = ELU(alpha=1).  tcgen05 tensor cores with 3xTF32 operand splitting (fp32-equivalent: relative

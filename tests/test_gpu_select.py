@@ -185,3 +185,53 @@ def test_lgnet_knn_new_k40():
         safe = (v[:, :, 39] - v[:, :, 40]) > 1e-5 * v[:, :, 40].abs()            # rows whose 40th / 41st neighbours are not a near-tie
         same = (idx.sort(-1).values == ref[:, :, :40].sort(-1).values).all(-1)
         assert safe.float().mean() > 0.95 and bool(same[safe].all()), (n, c, float(safe.float().mean()), int((~same & safe).sum()))
+
+
+def test_lgnet_sa_attention_without_the_matrix():
+    """SURVEY 8 row f1, SA_Layer (models/model.py:113-123): (a) `lgnet.sa_attention` (row chunks: tcgen05 GEMM -> fused softmax +
+    transpose -> tcgen05 GEMM, column sums from an appended row of ones) against the dense fp64 formula, several chunkings incl. a
+    ragged last chunk and N not a multiple of 4; (b) `lgnet.sa_layer_forward` on a module with the reference layer's weights
+    against the output of the unmodified reference layer."""
+    import os
+    import numpy as np
+    from dv_matcher_b200 import lgnet
+    from oracle import lgnet as ol
+    gen = torch.Generator().manual_seed(3)
+    for B, N, c, C, chunk in ((2, 701, 32, 128, 256), (1, 4995, 32, 128, 2048), (1, 1030, 16, 64, 4096), (1, 9000, 32, 128, 2048)):
+        q = torch.randn(B, N, c, generator=gen) * 0.7
+        k = q.permute(0, 2, 1).contiguous()                                  # SA_Layer ties q_conv and k_conv: energy is symmetric
+        v = torch.randn(B, C, N, generator=gen)
+        ref = ol.sa_attention_dense(q.double(), k.double(), v.double())
+        got = lgnet.sa_attention(q.cuda(), k.cuda(), v.cuda(), chunk=chunk).cpu()
+        err = (got.double() - ref).abs().max().item() / ref.abs().max().item()
+        dense32 = ol.sa_attention_dense(q.cuda(), k.cuda(), v.cuda()).cpu()             # what stock fp32 PyTorch gives on the same GPU
+        err32 = (dense32.double() - ref).abs().max().item() / ref.abs().max().item()
+        _report("lgnet_sa_attention", N=N, chunk=chunk, rel_err=err, torch_fp32_dense_rel_err=err32)
+        assert err <= 1e-4, (N, chunk, err)              # fp32 tolerance; the exponentials amplify the 1e-6 score rounding by |energy|
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_lgnet.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd_")}
+
+    class Layer(torch.nn.Module):                                            # SA_Layer's modules (models/model.py:98-111)
+        def __init__(self, ch=128):
+            super().__init__()
+            self.q_conv = torch.nn.Conv1d(ch, ch // 4, 1, bias=False)
+            self.k_conv = torch.nn.Conv1d(ch, ch // 4, 1, bias=False)
+            self.v_conv = torch.nn.Conv1d(ch, ch, 1)
+            self.trans_conv = torch.nn.Conv1d(ch, ch, 1)
+            self.after_norm = torch.nn.BatchNorm1d(ch)
+            self.act = torch.nn.ReLU()
+            self.softmax = torch.nn.Softmax(dim=-1)
+
+    layer = Layer()
+    layer.load_state_dict({k: v for k, v in sd.items() if not k.startswith(("bn1", "conv1"))}, strict=True)
+    layer = layer.cuda().eval()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                                  # the 1x1 convolutions around the attention stay torch's
+    try:
+        with torch.no_grad():
+            y = lgnet.sa_layer_forward(layer, torch.from_numpy(z["x"]).cuda()).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    err = (y - torch.from_numpy(z["y"])).abs().max().item() / float(np.abs(z["y"]).max())
+    _report("lgnet_sa_layer", rel_err=err)
+    assert err <= 1e-5, err

@@ -172,3 +172,13 @@ def test_secondary_api_matches_reference():
     assert torch.equal(src, t["source_cross_recon"]) and torch.equal(tgt, t["target_cross_recon"])
     assert torch.equal(osec.forward_shape(t["feat_source"], t["vert_source"]), t["self_recon"])
     assert torch.equal(osec.cross_construct(t["feat_source"], t["feat_target"], t["vert_target"], 10), t["cross_construct"])
+
+
+def test_lgnet_sa_layer_matches_reference():
+    """oracle/lgnet.py against the unmodified reference's SA_Layer (tests/golden/make_golden_lgnet.py)."""
+    import os
+    from oracle import lgnet as ol
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_lgnet.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd_")}
+    y = ol.sa_layer(torch.from_numpy(z["x"]), sd)
+    assert torch.equal(y, torch.from_numpy(z["y"]))
