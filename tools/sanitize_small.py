@@ -42,3 +42,12 @@ if graph is not None:
     out = dg.deform_from_d9(verts, graph, d9, want_sr=True)
 torch.cuda.synchronize()
 print("ok2", o4.stats.cpu().tolist(), float(gx.abs().max()), float((gx - gx32).abs().max()))
+# ---- secondary API, LG-Net attention
+from dv_matcher_b200 import secondary, lgnet
+fs = torch.randn(1, 420, 32).cuda(); ft = torch.randn(1, 360, 32).cuda()
+secondary.forward_source_target(fs, ft, torch.randn(1, 420, 3).cuda(), torch.randn(1, 360, 3).cuda())
+secondary.cross_construct(fs, ft, torch.randn(1, 360, 3).cuda(), 10)
+qq = torch.randn(1, 701, 32).cuda() * 0.5
+xr = lgnet.sa_attention(qq, qq.permute(0, 2, 1).contiguous(), torch.randn(1, 64, 701).cuda(), chunk=256)
+torch.cuda.synchronize()
+print("ok3", float(xr.abs().max()))
