@@ -63,6 +63,8 @@ SIGNATURES = {
     "dvm_gather_rows_fwd": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
     "dvm_gather_rows_bwd": (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
     "dvm_softmax_rows_transposed": (c_int, [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
+    "dvm_softmax_rows_inplace": (c_int, [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
+    "dvm_attn_softmax_bwd": (c_int, [c_void_p] * 4 + [c_int, c_int, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "dvm_linear_act_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

@@ -67,6 +67,70 @@ softmax_rows_transposed_kernel(const float* __restrict__ E, int rows, int N, lon
     }
 }
 
+// ---- backward of the same attention (training at sizes where the N x N matrices do not fit) -----------------------------------
+// With P = softmax_rows(E), s_j = sum_i P_ij, t_j = 1 / (1e-9 + s_j), A_ij = P_ij t_j, x_r = x_v A and G = dL/dx_r:
+//   dA_ij = sum_c x_v[c,i] G[c,j]                       (GEMM per row chunk)
+//   w_j   = sum_i dA_ij A_ij = sum_c G[c,j] x_r[c,j]    (no N x N sum needed)
+//   dP_ij = t_j (dA_ij - w_j)                           (through A = P t and s_j)
+//   dE_ij = P_ij (dP_ij - sum_j' P_ij' dP_ij')          (row softmax)
+// softmax_rows_inplace_kernel turns an energy chunk into P; attn_bwd_rowdot_kernel / attn_bwd_write_kernel turn (P, dA) into dE,
+// in place over dA and transposed into dEt (the operand layout of the dK GEMM).
+__global__ void __launch_bounds__(256)
+softmax_rows_inplace_kernel(float* __restrict__ E, int rows, int N, long long pitch, const float* __restrict__ stats) {
+    const int r = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j < N) {
+        float* e = E + (size_t)r * pitch + j;
+        *e = expf(*e - __ldg(stats + 2 * r)) * __ldg(stats + 2 * r + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+attn_bwd_rowdot_kernel(const float* __restrict__ P, const float* __restrict__ dA, const float* __restrict__ t, const float* __restrict__ w,
+                       int rows, int N, long long pitch, float* __restrict__ rowdot) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float* p = P + (size_t)r * pitch;
+    const float* d = dA + (size_t)r * pitch;
+    float acc = 0.f;
+    for (int j = lane; j < N; j += 32) acc = fmaf(__ldg(p + j), __ldg(t + j) * (__ldg(d + j) - __ldg(w + j)), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) rowdot[r] = acc;
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+attn_bwd_write_kernel(const float* __restrict__ P, float* __restrict__ dA_dE, const float* __restrict__ t, const float* __restrict__ w,
+                      const float* __restrict__ rowdot, int rows, int N, long long pitch, float* __restrict__ dEt, long long dEt_pitch) {
+    __shared__ float s_rd[SM_ROWS];
+    __shared__ float tile[SM_ROWS][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * SM_ROWS;
+    const int c_lo = blockIdx.y * SM_COLS, c_hi = min(N, c_lo + SM_COLS);
+    if (threadIdx.x < SM_ROWS) s_rd[threadIdx.x] = r0 + threadIdx.x < rows ? rowdot[r0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    for (int j0 = c_lo; j0 < c_hi; j0 += 32) {
+#pragma unroll
+        for (int q = 0; q < SM_ROWS / 8; ++q) {
+            const int rl = wid * (SM_ROWS / 8) + q, r = r0 + rl, j = j0 + lane;
+            float v = 0.f;
+            if (r < rows && j < c_hi) {
+                const size_t o = (size_t)r * pitch + j;
+                v = __ldg(P + o) * (__ldg(t + j) * (dA_dE[o] - __ldg(w + j)) - s_rd[rl]);
+                dA_dE[o] = v;
+            }
+            tile[rl][lane] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jl = wid * 4 + q, j = j0 + jl;
+            if (j < c_hi && r0 + lane < rows) dEt[(size_t)j * dEt_pitch + r0 + lane] = tile[lane][jl];
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace dvm
 
 using namespace dvm;
@@ -80,6 +144,29 @@ extern "C" int dvm_softmax_rows_transposed(const float* E, int rows, int N, long
     softmax_row_stats_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(E, rows, N, pitch, stats);
     DVM_LAUNCH_CHECK();
     softmax_rows_transposed_kernel<<<dim3(ceil_div(rows, SM_ROWS), ceil_div(N, SM_COLS)), SM_THREADS, 0, st>>>(E, rows, N, pitch, stats, Pt, pt_pitch);
+    DVM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dvm_softmax_rows_inplace(float* E, int rows, int N, long long pitch, float* stats, void* stream) {
+    DVM_CHECK_ARG(E && stats, "dvm_softmax_rows_inplace: null pointer");
+    DVM_CHECK_ARG(rows > 0 && rows <= 65535 && N > 0 && pitch >= N, "dvm_softmax_rows_inplace: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    softmax_row_stats_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(E, rows, N, pitch, stats);
+    DVM_LAUNCH_CHECK();
+    softmax_rows_inplace_kernel<<<dim3(ceil_div(N, 256), rows), 256, 0, st>>>(E, rows, N, pitch, stats);
+    DVM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dvm_attn_softmax_bwd(const float* P, float* dA_dE, const float* t, const float* w, int rows, int N, long long pitch,
+                                    float* dEt, long long dEt_pitch, float* rowdot, void* stream) {
+    DVM_CHECK_ARG(P && dA_dE && t && w && dEt && rowdot, "dvm_attn_softmax_bwd: null pointer");
+    DVM_CHECK_ARG(rows > 0 && N > 0 && pitch >= N && dEt_pitch >= rows && ceil_div(N, SM_COLS) <= 65535, "dvm_attn_softmax_bwd: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    attn_bwd_rowdot_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(P, dA_dE, t, w, rows, N, pitch, rowdot);
+    DVM_LAUNCH_CHECK();
+    attn_bwd_write_kernel<<<dim3(ceil_div(rows, SM_ROWS), ceil_div(N, SM_COLS)), SM_THREADS, 0, st>>>(P, dA_dE, t, w, rowdot, rows, N, pitch, dEt, dEt_pitch);
     DVM_LAUNCH_CHECK();
     return 0;
 }

@@ -232,6 +232,12 @@ int dvm_gather_rows_bwd(const float* d_out, const int64_t* idx, int B, int N, in
  * Middle step of LG-Net's SA_Layer attention without the N x N matrix (models/model.py:113-119; dv_matcher_b200/lgnet.py):
  * scores and the weighted sum on either side are dvm_linear_act_fwd GEMMs.  stats: scratch of 2 * rows floats (row max, 1 / row sum). */
 int dvm_softmax_rows_transposed(const float* E, int rows, int N, long long pitch, float* Pt, long long pt_pitch, float* stats, void* stream);
+/* Backward of that attention, per row chunk (csrc/attention.cu has the derivation): dvm_softmax_rows_inplace turns an energy chunk
+ * into P (rows <= 65535); dvm_attn_softmax_bwd turns (P, dA) into dE = P (t (dA - w) - rowdot), in place over dA and transposed
+ * into dEt[N][dEt_pitch].  t[N] = 1 / (1e-9 + column sums), w[N] = sum_c G[c,:] x_r[c,:]; rowdot: scratch of `rows` floats. */
+int dvm_softmax_rows_inplace(float* E, int rows, int N, long long pitch, float* stats, void* stream);
+int dvm_attn_softmax_bwd(const float* P, float* dA_dE, const float* t, const float* w, int rows, int N, long long pitch,
+                         float* dEt, long long dEt_pitch, float* rowdot, void* stream);
 
 /* One layer of the Deformer's decoder MLP (models/model.py:433-452: nn.Linear + nn.ELU; called at :476-477):
  *   out[r, n] = act( sum_k x[r,k] W[n,k] + bias[n] ),  x[rows][x_pitch] (K used), W[N][w_pitch] (nn.Linear layout),

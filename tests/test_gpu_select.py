@@ -235,3 +235,24 @@ def test_lgnet_sa_attention_without_the_matrix():
     err = (y - torch.from_numpy(z["y"])).abs().max().item() / float(np.abs(z["y"]).max())
     _report("lgnet_sa_layer", rel_err=err)
     assert err <= 1e-5, err
+
+
+def test_lgnet_sa_attention_backward_vs_autograd():
+    """Gradients of `lgnet.sa_attention` w.r.t. x_q, x_k, x_v against fp64 autograd of the reference's dense formula
+    (models/model.py:116-119), several chunkings."""
+    from dv_matcher_b200 import lgnet
+    from oracle import lgnet as ol
+    gen = torch.Generator().manual_seed(9)
+    for B, N, c, C, chunk in ((2, 701, 32, 128, 256), (1, 2500, 32, 128, 2048), (1, 1030, 16, 64, 4096)):
+        q = torch.randn(B, N, c, generator=gen) * 0.6
+        k = torch.randn(B, c, N, generator=gen) * 0.6
+        v = torch.randn(B, C, N, generator=gen)
+        coef = torch.randn(B, C, N, generator=gen)
+        qd, kd, vd = (a.double().requires_grad_(True) for a in (q, k, v))
+        (ol.sa_attention_dense(qd, kd, vd) * coef.double()).sum().backward()
+        qg, kg, vg = (a.cuda().requires_grad_(True) for a in (q, k, v))
+        (lgnet.sa_attention(qg, kg, vg, chunk=chunk) * coef.cuda()).sum().backward()
+        for name, got, ref in (("dQ", qg.grad, qd.grad), ("dK", kg.grad, kd.grad), ("dV", vg.grad, vd.grad)):
+            err = (got.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+            _report("lgnet_sa_attention_bwd", N=N, chunk=chunk, which=name, rel_err=err)
+            assert err <= 1e-4, (N, chunk, name, err)
