@@ -80,8 +80,8 @@ class CapturedTrainStep:
         self._fill(batch, graphs)
         if self.graph is None:
             cur = torch.cuda.current_stream()
-            side = torch.cuda.Stream()
-            side.wait_stream(cur)
+            side = self._capture_stream = torch.cuda.Stream()       # kept alive: the library's workspaces are keyed by stream, and the
+            side.wait_stream(cur)                                   # captured kernels hold raw pointers into this stream's buffers
             with torch.cuda.stream(side):                      # warm-up on the capture stream: workspaces, lazy initialisation
                 for _ in range(self.warmup):
                     for p in self.params:
