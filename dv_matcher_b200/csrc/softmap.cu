@@ -533,12 +533,15 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
         if (lane == s) { sel_key = f32_from_ordered(wk); sel_idx = wi; }
     }
     float key16 = __shfl_sync(0xffffffffu, sel_key, KC - 1);
+    float tp_min;
     {                                                                 // discard bounds of the partial lists
         float tp = lane < P ? a.cb.t[(size_t)g * P + lane] : INFINITY;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tp = fminf(tp, __shfl_xor_sync(0xffffffffu, tp, o));
+        tp_min = tp;
         key16 = fminf(key16, tp);
     }
+    const float l_base = l_tot;                                       // mass of everything outside the partial lists
     if (kSoft) {                                                      // listed but not selected: approximate terms
         float t = 0.f;
 #pragma unroll
@@ -552,16 +555,44 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) softmap_finalize_kernel(Finali
 
     // ---- certificate: every discarded column has candidate-pass key >= key16, i.e. a true distance of at least
     //      sqrt(key16 - E2) - (|x - x~| + |y - y~|) - rel * d16, E2 = accumulation error of the tensor-core key
-    if (lane == 0) {
-        float bound = 0.f, e2 = 0.f;
-        if (a.err_x) bound = a.err_x[g] + a.err_ymax[b];
-        if (a.tc_xx) e2 = 4e-6f * (a.tc_xx[g] + a.tc_yymax[b]);      // MMA accumulation + 16 ulp of packed list keys
-        bool ok;
-        if (key16 == INFINITY) ok = bound < INFINITY;            // every column is in the list (M < KC) unless the
-        else {                                                   // 16-bit conversion overflowed
-            const float d16 = sqrtf(fmaxf(key16 - e2, 0.f));
-            ok = dk < d16 - (bound + a.rel_bound * d16);
+    float bound = 0.f, e2 = 0.f;
+    if (a.err_x) bound = a.err_x[g] + a.err_ymax[b];
+    if (a.tc_xx) e2 = 4e-6f * (a.tc_xx[g] + a.tc_yymax[b]);          // MMA accumulation + 16 ulp of packed list keys
+    auto certified = [&](float dkk, float kb) {
+        if (kb == INFINITY) return bound < INFINITY;                  // every column is in the list (M < KC) unless the
+        const float db = sqrtf(fmaxf(kb - e2, 0.f));                  // 16-bit conversion overflowed
+        return dkk < db - (bound + a.rel_bound * db);
+    };
+    bool ok = certified(dk, key16);
+    // ---- second chance (warp-uniform): the union of the partial lists holds more than the KC re-scored candidates.  Re-score the
+    //      next KC of them too: the bound on what was DISCARDED then is the lists' discard bound (and the key of a 33rd entry, if
+    //      any) instead of the 16th candidate's key -- about twice the gap, for 32 more row loads of a row that would otherwise
+    //      cost a threshold scan over all M columns.
+    if (!ok && __any_sync(0xffffffffu, eo[0] != 0xffffffffu)) {
+        for (int s = KC; s < 2 * KC; ++s) {
+            const unsigned wk = __reduce_min_sync(0xffffffffu, eo[0]);
+            if (wk == 0xffffffffu) break;
+            const int wi = __reduce_min_sync(0xffffffffu, eo[0] == wk ? ei[0] : 0x7fffffff);
+            if (eo[0] == wk && ei[0] == wi) {
+                eo[0] = eo[1]; ei[0] = ei[1]; eo[1] = eo[2]; ei[1] = ei[2]; eo[2] = eo[3]; ei[2] = ei[3]; eo[3] = 0xffffffffu; ei[3] = 0x7fffffff;
+            }
+            if (lane == s) { sel_key = f32_from_ordered(wk); sel_idx = wi; }
         }
+        const unsigned rest = __reduce_min_sync(0xffffffffu, eo[0]);   // best key still unselected (a 33rd entry), if any
+        const float key_rest = fminf(rest == 0xffffffffu ? INFINITY : f32_from_ordered(rest), tp_min);
+        float l2 = l_base;
+        if (kSoft) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (eo[q] != 0xffffffffu) t += exp2f(-a2 * (sqrtf(f32_from_ordered(eo[q])) - r_star));
+            l2 += warp_sum(t);
+        }
+        rescore_emit<kSoft>(a, g, b, lane, sel_idx, 2 * KC, l2, r_star, dk, dmin);
+        l_tot = l2;
+        ok = certified(dk, key_rest);
+    }
+    if (lane == 0) {
         // the 16-bit pass sums its softmax mass against a FIXED per-row reference (the priming pass' sampled minimum): a row
         // without a finite sample, or one whose terms overflowed against it, has a non-finite mass and is settled exactly
         if (kSoft && !(l_tot < INFINITY)) { ok = false; if (a.nonfinite_count) atomicAdd(a.nonfinite_count, 1); }
