@@ -221,3 +221,51 @@ def test_bench_product_arm_refuses_to_run_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
     assert "no CPU fallback" in (out.stdout + out.stderr)
     assert not any(l.startswith("{") for l in out.stdout.splitlines())
+
+
+def test_install_patches_lgnet_attention_and_cpu_path_matches_reference():
+    """install() rebinds LG-Net's N x N pieces: `models.model.knn_new`, `index_points` and `SA_Layer.forward`.
+    On CPU tensors the patched forward runs the reference's dense formula: its output on the reference layer's weights equals the
+    unmodified reference's output (tests/golden/ref_lgnet.npz)."""
+    from dv_matcher_b200 import install as inst, geometry, lgnet
+
+    class SA_Layer(torch.nn.Module):                                   # the reference layer's modules (models/model.py:98-111)
+        def __init__(self, ch=128):
+            super().__init__()
+            self.q_conv = torch.nn.Conv1d(ch, ch // 4, 1, bias=False)
+            self.k_conv = torch.nn.Conv1d(ch, ch // 4, 1, bias=False)
+            self.v_conv = torch.nn.Conv1d(ch, ch, 1)
+            self.trans_conv = torch.nn.Conv1d(ch, ch, 1)
+            self.after_norm = torch.nn.BatchNorm1d(ch)
+            self.act = torch.nn.ReLU()
+            self.softmax = torch.nn.Softmax(dim=-1)
+
+        def forward(self, x):
+            raise AssertionError("the original forward must have been replaced")
+
+    fake = types.ModuleType("models.model")
+    fake.SA_Layer, fake.knn_new, fake.index_points, fake.Deformer = SA_Layer, object(), object(), object()
+    pkg = types.ModuleType("models")
+    saved = {k: sys.modules.get(k) for k in ("models", "models.model")}
+    sys.modules.update({"models": pkg, "models.model": fake})
+    try:
+        done = inst.install(import_missing=False)
+        assert done["models.model"] == 4
+        assert fake.knn_new is geometry.knn and fake.index_points is geometry.index_points
+        assert SA_Layer.forward is lgnet.sa_layer_forward
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ref_lgnet.npz"))
+        sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd_") and not k.startswith(("sd_bn1", "sd_conv1"))}
+        layer = SA_Layer()
+        layer.load_state_dict(sd, strict=True)
+        layer.eval()
+        with torch.no_grad():
+            y = layer(torch.from_numpy(z["x"]))
+        assert torch.allclose(y, torch.from_numpy(z["y"]), rtol=0, atol=1e-6)
+        inst.uninstall()
+        assert SA_Layer.forward is not lgnet.sa_layer_forward
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
