@@ -11,12 +11,15 @@ no data-path collective (torch.distributed is only used for the barrier and the 
 Prints ONE JSON line (rank 0).
 
 What is timed how:
-  value          K replays of the warm step captured as ONE CUDA graph per input batch (inputs resident in HBM);
+  value          K replays of the warm step captured as ONE CUDA graph per input batch (inputs resident in HBM); consecutive batches
+                 alternate over `--streams` compute streams (own workspaces and graph pools), so the issue-bound tail of one step
+                 overlaps the tensor-bound sweep of the next; every step's work is inside the timed region (K steps between two
+                 events bracketed by device synchronisation), ms_per_step = that time / K;
   roofline*      the same K steps launched eagerly with CUDA-event brackets inside the library, on the launching stream:
                  `roofline` = the dominant kernel (priming + sweep of the similarity pass), `roofline_fused` = the whole
                  fused op dvm_softmap_fwd (prep + prime + sweep + finalize + rescue), both against the measured bf16 peak;
   roofline_hbm   the memory-bound kernels alone at N = 200k x B = 32 (inputs > L2), algorithmic bytes / CUDA-event time;
-  e2e            MatchDeformEngine.submit/result with pinned HOST buffers: H2D of the inputs and D2H of the step's results
+  e2e            MatchDeformEngine.submit/result with pinned HOST buffers, up to four steps in flight: H2D of the inputs and D2H of the step's results
                  (hard maps, soft map idx + w, transferred and deformed coordinates, losses) inside the timed region;
   cpu_baseline / torch_cuda_baseline   the reference's torch op sequence (oracle port) on the host cores / on the same B200.
 """
