@@ -16,8 +16,14 @@ from . import ops
 
 
 def _unit(f):
+    """Rows scaled to unit length; the channel count is padded with zeros to a multiple of 4 (the kernels read float4 rows;
+    zeros change neither dot products nor distances)."""
     f = f.float()
-    return (f / f.norm(dim=-1)[:, :, None]).contiguous()
+    f = f / f.norm(dim=-1)[:, :, None]
+    pad = (-f.shape[-1]) % 4
+    if pad:
+        f = torch.nn.functional.pad(f, (0, pad))
+    return f.contiguous()
 
 
 def cosine_topk(a, b, k):
@@ -75,6 +81,9 @@ def cross_construct(x, y, verts2, k_num):
     """test_partial.py:134-144: the k_num nearest columns (exact-form distance), softmax of their cosine similarities."""
     x, y = x.float().contiguous(), y.float().contiguous()
     B, N, _ = x.shape
+    pad = (-x.shape[-1]) % 4
+    if pad:                                          # zero channels change no distance
+        x, y = torch.nn.functional.pad(x, (0, pad)), torch.nn.functional.pad(y, (0, pad))
     if k_num <= 10:
         idx = ops.softmap_fwd(x, y, None, alpha=1.0, topk=k_num, soft=True, prec="fp32").top_idx.long()     # exact, ascending distance
     else:

@@ -256,3 +256,19 @@ def test_lgnet_sa_attention_backward_vs_autograd():
             err = (got.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
             _report("lgnet_sa_attention_bwd", N=N, chunk=chunk, which=name, rel_err=err)
             assert err <= 1e-4, (N, chunk, name, err)
+
+
+def test_secondary_api_odd_channel_count():
+    """Channel counts that are not a multiple of 4 are zero-padded: same result as the dense formula."""
+    from dv_matcher_b200 import secondary
+    from oracle import secondary as osec
+    gen = torch.Generator().manual_seed(21)
+    fs, ft = torch.randn(1, 300, 30, generator=gen), torch.randn(1, 260, 30, generator=gen)
+    vs, vt = torch.randn(1, 300, 3, generator=gen), torch.randn(1, 260, 3, generator=gen)
+    a, b = secondary.forward_source_target(fs.cuda(), ft.cuda(), vs.cuda(), vt.cuda(), k=20)
+    ra, rb = osec.forward_source_target(fs.double(), ft.double(), vs.double(), vt.double(), k=20)
+    c = secondary.cross_construct(fs.cuda(), ft.cuda(), vt.cuda(), 7)
+    rc = osec.cross_construct(fs, ft, vt, 7)
+    for got, ref in ((a, ra), (b, rb), (c, rc)):
+        err = (got.cpu().double() - ref.double()).abs().amax(-1)
+        assert (err > 1e-4).float().mean().item() <= 0.01          # a near-tie at the selection boundary may swap one neighbour
